@@ -1,0 +1,1215 @@
+// frecsys CPU oracle — TEST INFRASTRUCTURE ONLY.
+//
+// An Eigen-free CPU restatement of the per-epoch ALS hot path of
+// riktor/safer2-recommender (`frecsys`): iALS, iALS++, ERM-MF, CVaR-MF, SAFER2,
+// SAFER2++ plus the fold-in Recall/NDCG evaluation.  Only tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+// may build, link or call anything in oracle/.  The product path
+// (safer2-recommender_b200/csrc, include/) never includes this file.
+//
+// PARITY STATUS: "parity unpinned" at the numeric level.  The reference holds
+// no golden vectors and seeds from std::random_device; its arithmetic lives in
+// Eigen 3.4.0 (WORKSPACE:39-47), which is not vendored and absent from this
+// image, so the reference itself cannot be built here.  What pins this oracle:
+//  * the reference's own test thresholds on its bundled ML-1M fixture
+//    (NDCG@20 >= 0.2, tests/ials_test.cc:45 ...; |mean z - alpha| <= 0.02,
+//    tests/safer2_test.cc:135) -> tests/test_oracle_reference_thresholds.py
+//  * a line-by-line restatement of each function, cited below, including the
+//    behaviour-defining quirks (B-1 stale tail, B-3/B-4
+//    CVaR-MF gradient, B-6 Armijo, B-7 CVaR xi0, B-14 float fabs).
+//
+// Eigen semantics relied on (upstream 3.4.0): MatrixXf here is ROW-major
+// (types.h:25-27); selfadjointView<Lower>().rankUpdate(X) adds X*X^T to the
+// lower triangle only; LLT<.,Lower> reads only the lower triangle;
+// ConjugateGradient<.,Lower> = Jacobi-preconditioned CG on the symmetric view,
+// x0 = 0.  Summation order inside Eigen's GEMM/reductions is not reproducible
+// and not required (tolerance 1e-4 rel. Frobenius); accumulators are `real`
+// (= float, the reference's type) unless built with -DORACLE_FP64.
+#pragma once
+
+#include <algorithm>
+#include <atomic>
+#include <cassert>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <limits>
+#include <numeric>
+#include <random>
+#include <set>
+#include <string>
+#include <thread>
+#include <tuple>
+#include <utility>
+#include <vector>
+
+namespace oracle {
+
+#ifdef ORACLE_FP64
+using real = double;
+#else
+using real = float;
+#endif
+
+using SpVector = std::vector<std::pair<int, int>>;  // types.h:30
+
+// ---------------------------------------------------------------------------
+// Dataset — restates dataset.h:71-99.  by_user[u] / by_item[i] hold
+// (other_id, tuple_index) in FILE order; the reference keys an unordered_map
+// by id, here rows are indexed by id and absent ids have empty vectors.
+// ---------------------------------------------------------------------------
+struct Dataset {
+  std::vector<SpVector> by_user, by_item;
+  int max_user = -1, max_item = -1, num_tuples = 0;
+  int distinct_users = 0, distinct_items = 0;
+
+  void add(int user, int item) {  // dataset.h:86-91
+    if (user >= (int)by_user.size()) by_user.resize(user + 1);
+    if (item >= (int)by_item.size()) by_item.resize(item + 1);
+    if (by_user[user].empty()) ++distinct_users;
+    if (by_item[item].empty()) ++distinct_items;
+    by_user[user].push_back({item, num_tuples});
+    by_item[item].push_back({user, num_tuples});
+    max_user = std::max(max_user, user);
+    max_item = std::max(max_item, item);
+    ++num_tuples;
+  }
+
+  static Dataset FromCsv(const std::string& filename) {
+    Dataset d;
+    std::ifstream infile(filename);
+    std::string line;
+    if (!std::getline(infile, line)) {  // dataset.h:80 header discarded
+      std::fprintf(stderr, "oracle: cannot read %s\n", filename.c_str());
+      std::abort();
+    }
+    while (std::getline(infile, line)) {  // dataset.h:83-92
+      int pos = line.find(',');
+      int user = std::atoi(line.substr(0, pos).c_str());
+      int item = std::atoi(line.substr(pos + 1).c_str());
+      d.add(user, item);
+    }
+    return d;
+  }
+
+  static Dataset FromTuples(const int* users, const int* items, int n) {
+    Dataset d;
+    for (int t = 0; t < n; ++t) d.add(users[t], items[t]);
+    return d;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Dense helpers (stand-ins for the Eigen calls; row-major float).
+// ---------------------------------------------------------------------------
+struct Mat {
+  int rows = 0, cols = 0;
+  std::vector<float> a;
+  Mat() {}
+  Mat(int r, int c) : rows(r), cols(c), a((size_t)r * c, 0.f) {}
+  float* row(int i) { return a.data() + (size_t)i * cols; }
+  const float* row(int i) const { return a.data() + (size_t)i * cols; }
+  float& operator()(int i, int j) { return a[(size_t)i * cols + j]; }
+  float operator()(int i, int j) const { return a[(size_t)i * cols + j]; }
+};
+
+inline int NumThreads() {
+  static int n = [] {
+    const char* e = std::getenv("ORACLE_THREADS");
+    int v = e ? std::atoi(e) : (int)std::thread::hardware_concurrency();
+    return v > 0 ? v : 1;
+  }();
+  return n;
+}
+
+// The reference's work queue: hardware_concurrency() threads pull the next row
+// under a mutex (safer2.h:445-487).  Rows are independent, so an atomic
+// counter over the id-ordered row list gives the same results.
+template <typename F>
+inline void ParallelFor(int n, F f) {
+  int nt = std::min(NumThreads(), std::max(n, 1));
+  if (nt <= 1) {
+    for (int i = 0; i < n; ++i) f(i);
+    return;
+  }
+  std::atomic<int> next{0};
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; ++t)
+    th.emplace_back([&] {
+      for (;;) {
+        int i = next.fetch_add(1);
+        if (i >= n) return;
+        f(i);
+      }
+    });
+  for (auto& x : th) x.join();
+}
+
+inline real Dot(const float* a, const float* b, int d) {
+  real s = 0;
+  for (int k = 0; k < d; ++k) s += (real)a[k] * (real)b[k];
+  return s;
+}
+
+// out(d x d) = sum_r w_r * E.row(r)[cs:cs+bd]^T * F.row(r)[:]   (w may be null)
+// Stand-in for `X.transpose() * Y` (ials.h:321, safer2.h:55,294,509; block
+// forms ialspp.h:356-365, safer2pp.h:534-544).  Rows are processed in panels
+// of 256 with per-panel partial sums, which is how a blocked GEMM accumulates.
+inline Mat GramianGeneral(const Mat& E, int cs, int bd, const Mat& F, int fs,
+                          int fd, const float* w) {
+  Mat out(bd, fd);
+  const int n = E.rows;
+  const int nt = std::min(NumThreads(), std::max(1, n / 2048));
+  std::vector<std::vector<real>> part(nt, std::vector<real>((size_t)bd * fd, 0));
+  auto work = [&](int t) {
+    int lo = (int)((long long)n * t / nt), hi = (int)((long long)n * (t + 1) / nt);
+    std::vector<real>& acc = part[t];
+    std::vector<real> panel((size_t)bd * fd);
+    for (int r0 = lo; r0 < hi; r0 += 256) {
+      std::fill(panel.begin(), panel.end(), (real)0);
+      int r1 = std::min(hi, r0 + 256);
+      for (int r = r0; r < r1; ++r) {
+        const float* e = E.row(r) + cs;
+        const float* f = F.row(r) + fs;
+        const real wr = w ? (real)w[r] : (real)1;
+        for (int i = 0; i < bd; ++i) {
+          const real ei = (real)e[i] * wr;
+          real* pr = panel.data() + (size_t)i * fd;
+          for (int j = 0; j < fd; ++j) pr[j] += ei * (real)f[j];
+        }
+      }
+      for (size_t k = 0; k < acc.size(); ++k) acc[k] += panel[k];
+    }
+  };
+  if (nt == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
+    for (auto& x : th) x.join();
+  }
+  for (int t = 0; t < nt; ++t)
+    for (size_t k = 0; k < out.a.size(); ++k) {
+      real v = (t == 0 ? (real)0 : (real)out.a[k]) + part[t][k];
+      out.a[k] = (float)v;
+    }
+  return out;
+}
+inline Mat Gramian(const Mat& E, const float* w = nullptr) {
+  return GramianGeneral(E, 0, E.cols, E, 0, E.cols, w);
+}
+
+// selfadjointView<Lower>().rankUpdate(F) with F = d x nb stored as nb rows of
+// d floats (column c of the reference's factor_batch = row c here).
+inline void RankUpdateLower(real* M, int d, const float* batch, int nb) {
+  for (int c = 0; c < nb; ++c) {
+    const float* f = batch + (size_t)c * d;
+    for (int i = 0; i < d; ++i) {
+      const real fi = f[i];
+      real* mr = M + (size_t)i * d;
+      for (int j = 0; j <= i; ++j) mr[j] += fi * (real)f[j];
+    }
+  }
+}
+
+// Eigen::LLT<MatrixXf, Lower>: in-place lower Cholesky reading only the lower
+// triangle, then forward/back substitution.  Returns false if
+// a pivot is <= 0 (the reference asserts, safer2.h:160).
+inline bool CholeskySolveLower(real* M, int d, real* b) {
+  for (int k = 0; k < d; ++k) {
+    real* rk = M + (size_t)k * d;
+    real x = rk[k];
+    for (int p = 0; p < k; ++p) x -= rk[p] * rk[p];
+    if (!(x > 0)) return false;
+    const real lkk = std::sqrt(x);
+    rk[k] = lkk;
+    const real inv = (real)1 / lkk;
+    for (int i = k + 1; i < d; ++i) {
+      real* ri = M + (size_t)i * d;
+      real s = ri[k];
+      for (int p = 0; p < k; ++p) s -= ri[p] * rk[p];
+      ri[k] = s * inv;
+    }
+  }
+  for (int i = 0; i < d; ++i) {  // L y = b
+    const real* ri = M + (size_t)i * d;
+    real s = b[i];
+    for (int p = 0; p < i; ++p) s -= ri[p] * b[p];
+    b[i] = s / ri[i];
+  }
+  for (int i = d - 1; i >= 0; --i) {  // L^T x = y
+    real s = b[i];
+    for (int p = i + 1; p < d; ++p) s -= M[(size_t)p * d + i] * b[p];
+    b[i] = s / M[(size_t)i * d + i];
+  }
+  return true;
+}
+
+// y = selfadjointView<Lower>(M) * x
+inline void SymvLower(const real* M, int d, const real* x, real* y) {
+  for (int i = 0; i < d; ++i) y[i] = 0;
+  for (int i = 0; i < d; ++i) {
+    const real* ri = M + (size_t)i * d;
+    real s = 0;
+    for (int j = 0; j < i; ++j) {
+      s += ri[j] * x[j];
+      y[j] += ri[j] * x[i];
+    }
+    y[i] += s + ri[i] * x[i];
+  }
+}
+
+// Eigen::ConjugateGradient<MatrixXf, Lower> with the default diagonal
+// preconditioner (call sites ials.h:134-138, safer2.h:153-157).
+inline void ConjugateGradientLower(const real* M, int d, const real* rhs, real* x,
+                                   float tol, int max_it) {
+  std::vector<real> r(rhs, rhs + d), p(d), z(d), t(d), dinv(d);
+  for (int i = 0; i < d; ++i) {
+    x[i] = 0;
+    real di = M[(size_t)i * d + i];
+    dinv[i] = di != 0 ? (real)1 / di : (real)1;
+  }
+  real rhs2 = 0;
+  for (int i = 0; i < d; ++i) rhs2 += rhs[i] * rhs[i];
+  if (rhs2 == 0) return;
+  const real threshold =
+      std::max<real>((real)tol * (real)tol * rhs2, std::numeric_limits<real>::min());
+  real res2 = rhs2;
+  if (res2 < threshold) return;
+  for (int i = 0; i < d; ++i) p[i] = dinv[i] * r[i];
+  real absNew = 0;
+  for (int i = 0; i < d; ++i) absNew += r[i] * p[i];
+  for (int it = 0; it < max_it; ++it) {
+    SymvLower(M, d, p.data(), t.data());
+    real pt = 0;
+    for (int i = 0; i < d; ++i) pt += p[i] * t[i];
+    const real alpha = absNew / pt;
+    for (int i = 0; i < d; ++i) {
+      x[i] += alpha * p[i];
+      r[i] -= alpha * t[i];
+    }
+    res2 = 0;
+    for (int i = 0; i < d; ++i) res2 += r[i] * r[i];
+    if (res2 < threshold) break;
+    for (int i = 0; i < d; ++i) z[i] = dinv[i] * r[i];
+    const real absOld = absNew;
+    absNew = 0;
+    for (int i = 0; i < d; ++i) absNew += r[i] * z[i];
+    const real beta = absNew / absOld;
+    for (int i = 0; i < d; ++i) p[i] = z[i] + beta * p[i];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Hyper-parameters (the run_model flags, run_model.cc:128-230).
+// ---------------------------------------------------------------------------
+enum ModelKind { kIALS = 0, kIALSpp = 1, kERMMF = 2, kCVaRMF = 3, kSAFER2 = 4, kSAFER2pp = 5 };
+
+struct Config {
+  int model = kIALS;
+  int dim = 8;
+  float reg = 0.002f, reg_exp = 1.0f, uobs_weight = 0.1f, stdev = 0.1f;
+  float alpha = 0.3f, bandwidth = 1.0f, stepsize = 0.1f;
+  int xi_iterations = 5, pd_iterations = 1;
+  int use_epanechnikov = 0, use_snr = 0;
+  float sampling_ratio = 0.1f;
+  int use_cg = 0;
+  float cg_tol = 1e-10f;
+  int cg_max_it = 100;
+  int block_size = 64;
+  unsigned snr_seed = 0;  // harness-injected (reference: random_device, safer2.h:728)
+};
+
+// Recommender::init_matrix (recommender.h:61-67): one mt19937, a fresh
+// normal_distribution<float>(0, stdev/sqrt(d)) per matrix, U first then V
+// (safer2.h:50-54).  The reference seeds from random_device; we inject.
+inline void InitFactors(Mat* U, Mat* V, float stdev, unsigned seed) {
+  const float adjusted = stdev / std::sqrt((double)U->cols);  // float / double sqrt(int), safer2.h:50
+  std::mt19937 gen{seed};
+  {
+    std::normal_distribution<float> d(0, adjusted);
+    for (auto& x : U->a) x = d(gen);
+  }
+  {
+    std::normal_distribution<float> d(0, adjusted);
+    for (auto& x : V->a) x = d(gen);
+  }
+}
+
+// Kernel functions, safer2.h:599-647 (dup. safer2pp.h:705-754).  Arguments and
+// returns are float, bodies evaluate in double exactly as the C++ promotions of
+// the reference expressions do.  B-14: float fabs.
+inline float gaussian_kernel(const float u, const float h) {
+  return std::pow(2 * M_PI, -0.5) * std::exp(-std::pow((u / h) * M_SQRT1_2, 2)) / h;
+}
+inline float gaussian_kernel_cdf(const float u, const float h) {
+  return 0.5 * std::erfc(-(u / h) * M_SQRT1_2);
+}
+inline float gaussian_loss(const float u, const float h, const float alpha) {
+  float ell = h * gaussian_kernel(u, h) + (u / h) * (1 - 2 * gaussian_kernel_cdf(-u, h));
+  return (h / 2) * ell + ((1 - alpha) - 0.5) * u;
+}
+inline float epanechnikov_kernel(const float u, const float h) {
+  float uh = u / h;
+  return (3.0 / 4.0) * (1 - std::pow((double)uh, 2)) * (int)(std::fabs(uh) < 1) / h;
+}
+inline float epanechnikov_kernel_cdf(const float u, const float h) {
+  float uh = u / h;
+  int in_supp = (int)(std::fabs(uh) <= 1);
+  int pos = (int)(uh > 1);
+  const double hd = h, ud = u;
+  float cdf = ((std::pow(hd, -3) / 4.0) *
+               (((3 * u) * std::pow(hd, 2) - std::pow(ud, 3)) + 2 * std::pow(hd, 3)) * in_supp) +
+              (1 - in_supp) * pos;
+  return cdf;
+}
+inline float epanechnikov_loss(const float u, const float h, const float alpha) {
+  float uh = u / h;
+  int in_supp = (int)(std::fabs(uh) <= 1);
+  int pos = (int)(uh > 1);
+  float ell = ((3.0 / 4.0) * std::pow((double)uh, 2) - (1.0 / 8.0) * std::pow((double)uh, 4) +
+               (3.0 / 8.0)) * in_supp +
+              std::fabs(uh) * pos;
+  return (1.0 / 2.0) * h * ell + ((1 - alpha) - 0.5) * u;
+}
+
+// Per-user evaluation result (evaluation.h:30-34).
+struct EvalResult {
+  std::vector<int> user_ids;   // row r of recall/ndcg belongs to user_ids[r]
+  std::vector<int> k_list;
+  Mat recall, ndcg;            // num_users x num_ks
+  std::vector<int> topk;       // num_users x max_k item ids (for top-k parity)
+  int max_k = 0;
+};
+
+// Recommender::EvaluateUser, recommender.h:132-199.
+inline void EvaluateUser(const std::vector<int>& k_list, std::vector<float> scores,
+                         const SpVector& ground_truth, const SpVector& exclude,
+                         float* recall_out, float* ndcg_out, int* topk_out) {
+  for (size_t i = 0; i < exclude.size(); ++i) {
+    assert(exclude[i].first < (int)scores.size());
+    scores[exclude[i].first] = std::numeric_limits<float>::lowest();
+  }
+  int max_k = *std::max_element(k_list.begin(), k_list.end());
+  std::vector<size_t> topk(scores.size());
+  std::iota(topk.begin(), topk.end(), 0);
+  std::nth_element(topk.begin(), topk.begin() + max_k, topk.end(),
+                   [&scores](size_t i1, size_t i2) { return scores[i1] > scores[i2]; });
+  std::stable_sort(topk.begin(), topk.begin() + max_k,
+                   [&scores](size_t i1, size_t i2) { return scores[i1] > scores[i2]; });
+  std::set<int> gt_set;
+  for (auto& p : ground_truth) gt_set.insert(p.first);
+  auto recall = [&](int k) -> float {
+    double result = 0.0;
+    for (int i = 0; i < k; ++i)
+      if (gt_set.find(topk[i]) != gt_set.end()) result += 1.0;
+    return result / std::min<float>(k, gt_set.size());
+  };
+  auto ndcg = [&](int k) -> float {
+    double result = 0.0;
+    for (int i = 0; i < k; ++i)
+      if (gt_set.find(topk[i]) != gt_set.end()) result += 1.0 / std::log2(i + 2.0);
+    double norm = 0.0;
+    for (int i = 0; i < std::min<int>(k, gt_set.size()); ++i) norm += 1.0 / std::log2(i + 2.0);
+    return result / norm;
+  };
+  for (size_t i = 0; i < k_list.size(); ++i) {
+    recall_out[i] = recall(k_list[i]);
+    ndcg_out[i] = ndcg(k_list[i]);
+  }
+  if (topk_out)
+    for (int i = 0; i < max_k; ++i) topk_out[i] = (int)topk[i];
+}
+
+// Loss statistics printed by PrintLosses / ComputeLosses.
+struct LossStats {
+  double loss = 0, loss_observed = 0, loss_unobserved = 0, loss_reg = 0;
+  double loss_reg_user = 0, loss_reg_item = 0;
+};
+
+// ---------------------------------------------------------------------------
+// The model: one class holding the state of whichever of the six recommenders
+// `cfg.model` selects; every method cites the reference function it restates.
+// ---------------------------------------------------------------------------
+class Model {
+ public:
+  Config cfg;
+  int num_users, num_items;
+  Mat U, V;                       // user_embedding_, item_embedding_
+  Mat item_gramian;               // item_gramian_ (safer2.h:55)
+  std::vector<float> user_loss, dual_weight, user_history_size, item_reg;
+  float prev_xi = 0.f;
+  int xi_calls = 0;               // for the injected SNR seed schedule
+  float last_weighted_loss = 0.f;
+  std::vector<std::vector<int>> last_snr_indices;  // what ComputeXi drew last
+  bool print_train_stats = false;
+  LossStats last_stats;
+
+  Model(const Config& c, int nu, int ni, unsigned init_seed)
+      : cfg(c), num_users(nu), num_items(ni), U(nu, c.dim), V(ni, c.dim) {
+    InitFactors(&U, &V, c.stdev, init_seed);
+    ResetState();
+  }
+
+  // Constructor tails: safer2.h:55-59, erm_mf.h:52-56, cvar_mf.h:50-54.
+  void ResetState() {
+    item_gramian = Gramian(V);
+    dual_weight.assign(num_users, cfg.alpha);
+    user_loss.assign(num_users, 0.f);
+    user_history_size.assign(num_users, 0.f);
+    item_reg.assign(num_items, 0.f);
+    prev_xi = 0.f;
+    xi_calls = 0;
+  }
+  void SetFactors(const float* u, const float* v) {
+    std::copy(u, u + U.a.size(), U.a.begin());
+    std::copy(v, v + V.a.size(), V.a.begin());
+    ResetState();
+  }
+
+  bool is_pp() const { return cfg.model == kIALSpp || cfg.model == kSAFER2pp; }
+  bool is_ials_family() const { return cfg.model == kIALS || cfg.model == kIALSpp; }
+
+  // ---- regularisation values ------------------------------------------------
+  // ials.h:310-315 / ialspp.h RegularizationValue: double pow, float return.
+  float IalsReg(int history_size, int num_choices) const {
+    return cfg.reg * std::pow((double)(float)(history_size + cfg.uobs_weight * num_choices),
+                              (double)cfg.reg_exp);
+  }
+  // safer2.h:418-421 (erm_mf.h:384-387, cvar_mf.h, safer2pp.h).
+  float UserReg(int num_choices) const { return cfg.reg * (1 + cfg.uobs_weight * num_choices); }
+  // safer2.h:426-432.
+  float ItemReg(int item, int num_choices) const {
+    float loss_weights = item_reg[item];
+    return cfg.reg * (loss_weights + cfg.alpha * cfg.uobs_weight * num_choices);
+  }
+
+  // ---- per-user loss ----------------------------------------------------------
+  // safer2.h:85-101 (erm_mf.h:73-89, cvar_mf.h:70-86); ials.h:70-86 and
+  // ialspp.h omit the final /2.  `pred` non-null = safer2pp.h:80-95 (cached
+  // predictions instead of dot products).
+  float ComputeLoss(const SpVector& hist, const float* u, const Mat& items, const Mat& G,
+                    float beta, bool halve, const float* pred) const {
+    const int d = items.cols;
+    float loss = 0;
+    for (const auto& ir : hist) {
+      float p = pred ? pred[ir.second] : (float)Dot(items.row(ir.first), u, d);
+      loss += std::pow((double)(p - 1), 2.0);  // float += double
+    }
+    loss /= hist.size();
+    real ireg_acc = 0;  // u^T G u as (u^T G) . u
+    for (int j = 0; j < d; ++j) {
+      real s = 0;
+      for (int i = 0; i < d; ++i) s += (real)u[i] * (real)G(i, j);
+      ireg_acc += s * (real)u[j];
+    }
+    float ireg = (float)ireg_acc;
+    loss += beta * ireg;
+    if (halve) loss /= 2.0;
+    return loss;
+  }
+
+  // ComputeUserLoss: safer2.h:558-596 (gramian passed in); ials.h:367-408
+  // recomputes the Gramian itself (caller passes it here).
+  void ComputeUserLoss(const Dataset& data, const Mat& G, const float* pred) {
+    const bool halve = !is_ials_family();
+    ParallelFor((int)data.by_user.size(), [&](int u) {
+      const SpVector& h = data.by_user[u];
+      if (h.empty()) return;
+      user_loss[u] = ComputeLoss(h, U.row(u), V, G, cfg.uobs_weight, halve, pred);
+    });
+  }
+
+  // ---- full-dimension projections -------------------------------------------
+  // Shared accumulation loop of every Project*: gather rows, rhs += w*row,
+  // factor_batch column = sqrt(w)*row, rankUpdate every kMaxBatchSize=128
+  // (ials.h:107-131, safer2.h:116-147,177-208).  `stale_tail` replicates B-1:
+  // safer2.h:200-204 / erm_mf.h:187-191 / cvar_mf.h:169-173 call
+  // rankUpdate(factor_batch) — all 128 columns — for the remainder batch, so
+  // the stale columns [num_batched,128) of the previous full batch are added
+  // a second time.
+  void Accumulate(const SpVector& hist, const Mat& E, int cs, int bd, const float* w_of,
+                  bool stale_tail, const float* pred, real* M, real* rhs) const {
+    const int kMaxBatchSize = 128;
+    const int batch_size = std::min((int)hist.size(), kMaxBatchSize);
+    std::vector<float> batch((size_t)batch_size * bd);
+    int num_batched = 0;
+    for (const auto& ir : hist) {
+      const int cp = ir.first;
+      const float* e = E.row(cp) + cs;
+      const float w = w_of ? w_of[cp] : 1.f;
+      // rhs: ials/safer2 `rhs += w*cp_v`; ++ variants `rhs += cp_v*residual(*w)`
+      // (ialspp.h:118-121, safer2pp.h:121-124,186-189).
+      float coef = w;
+      if (pred) {
+        const float residual = (pred[ir.second] - 1.0);
+        coef = w_of ? residual * w : residual;
+      }
+      for (int k = 0; k < bd; ++k) rhs[k] += (real)(coef * e[k]);
+      const float sw = w_of ? std::sqrt(w) : 1.f;
+      float* col = batch.data() + (size_t)num_batched * bd;
+      for (int k = 0; k < bd; ++k) col[k] = sw * e[k];
+      ++num_batched;
+      if (num_batched == batch_size) {
+        RankUpdateLower(M, bd, batch.data(), batch_size);
+        num_batched = 0;
+      }
+    }
+    if (num_batched != 0)
+      RankUpdateLower(M, bd, batch.data(), stale_tail ? batch_size : num_batched);
+  }
+
+  bool Solve(real* M, int d, real* rhs, real* x) const {
+    if (cfg.use_cg && (cfg.model == kIALS || cfg.model == kSAFER2 || cfg.model == kERMMF)) {
+      // ERM-MF's BiCGSTAB-on-unsymmetrised-matrix (B-5, erm_mf.h:139-145) is not
+      // restated; ERM-MF --use_cg falls to the symmetric CG here.
+      ConjugateGradientLower(M, d, rhs, x, cfg.cg_tol, cfg.cg_max_it);
+      return true;
+    }
+    bool ok = CholeskySolveLower(M, d, rhs);
+    for (int i = 0; i < d; ++i) x[i] = rhs[i];
+    return ok;
+  }
+
+  // IALSRecommender::Project, ials.h:88-144.
+  void ProjectIals(const SpVector& hist, const Mat& E, const Mat& G, float reg, float* out) const {
+    const int d = E.cols;
+    std::vector<real> M((size_t)d * d), rhs(d, 0), x(d);
+    for (int i = 0; i < d; ++i)
+      for (int j = 0; j < d; ++j) M[(size_t)i * d + j] = cfg.uobs_weight * G(i, j);
+    for (int i = 0; i < d; ++i) M[(size_t)i * d + i] += reg;
+    Accumulate(hist, E, 0, d, nullptr, false, nullptr, M.data(), rhs.data());
+    bool ok = Solve(M.data(), d, rhs.data(), x.data());
+    assert(ok); (void)ok;
+    for (int i = 0; i < d; ++i) out[i] = (float)x[i];
+  }
+
+  // Builds the SAFER2/ERM/CVaR user-side system, safer2.h:104-150:
+  // M = weight*(A/n + uw*G) + reg*I (lower), rhs = (weight/n) * sum v.
+  void BuildUserSystem(const SpVector& hist, const Mat& E, const Mat& G, float reg, float weight,
+                       real* M, real* rhs) const {
+    const int d = E.cols;
+    const int n = (int)hist.size();
+    std::fill(M, M + (size_t)d * d, (real)0);
+    std::fill(rhs, rhs + d, (real)0);
+    Accumulate(hist, E, 0, d, nullptr, false, nullptr, M, rhs);
+    for (size_t k = 0; k < (size_t)d * d; ++k) M[k] /= (float)n;       // matrix /= history_size
+    for (int i = 0; i < d; ++i)
+      for (int j = 0; j < d; ++j) M[(size_t)i * d + j] += cfg.uobs_weight * G(i, j);
+    for (size_t k = 0; k < (size_t)d * d; ++k) M[k] *= weight;         // matrix *= weight
+    const float s = weight / n;                                          // rhs *= weight / n
+    for (int i = 0; i < d; ++i) rhs[i] *= s;
+    for (int i = 0; i < d; ++i) M[(size_t)i * d + i] += reg;
+  }
+
+  // SAFER2Recommender::ProjectU safer2.h:104-163 (= erm_mf.h:91-151,
+  // cvar_mf.h:182-229 ProjectU_eval).
+  void ProjectU(const SpVector& hist, const Mat& E, const Mat& G, float reg, float weight,
+                float* out) const {
+    const int d = E.cols;
+    std::vector<real> M((size_t)d * d), rhs(d), x(d);
+    BuildUserSystem(hist, E, G, reg, weight, M.data(), rhs.data());
+    bool ok = Solve(M.data(), d, rhs.data(), x.data());
+    assert(ok); (void)ok;
+    for (int i = 0; i < d; ++i) out[i] = (float)x[i];
+  }
+
+  // Item-side system, safer2.h:166-208: M = uw*G + sum w u u^T (+B-1) + reg*I.
+  void BuildItemSystem(const SpVector& hist, const Mat& E, const Mat& G, float reg,
+                       const float* norm_w, real* M, real* rhs) const {
+    const int d = E.cols;
+    for (int i = 0; i < d; ++i)
+      for (int j = 0; j < d; ++j) M[(size_t)i * d + j] = cfg.uobs_weight * G(i, j);
+    std::fill(rhs, rhs + d, (real)0);
+    Accumulate(hist, E, 0, d, norm_w, /*stale_tail=*/true, nullptr, M, rhs);
+    for (int i = 0; i < d; ++i) M[(size_t)i * d + i] += reg;
+  }
+
+  // SAFER2Recommender::ProjectV safer2.h:166-221 (= erm_mf.h:153-210).
+  void ProjectV(const SpVector& hist, const Mat& E, const Mat& G, float reg, const float* norm_w,
+                float* out) const {
+    const int d = E.cols;
+    std::vector<real> M((size_t)d * d), rhs(d), x(d);
+    BuildItemSystem(hist, E, G, reg, norm_w, M.data(), rhs.data());
+    bool ok = Solve(M.data(), d, rhs.data(), x.data());
+    assert(ok); (void)ok;
+    for (int i = 0; i < d; ++i) out[i] = (float)x[i];
+  }
+
+  // CVaR-MF gradient step `x - stepsize * (matrix * x - rhs)` with the FULL
+  // matrix whose strict upper triangle never received the rankUpdate (B-3),
+  // cvar_mf.h:133,179.
+  static void GradStepFullMatrix(const real* M_lower_syrk, const Mat& G, float g_scale, int d,
+                                 const real* rhs, const float* x, float step, float* out) {
+    // M_lower_syrk holds the complete reference `matrix` in its lower triangle
+    // and diagonal; the strict upper triangle of the reference matrix is
+    // g_scale*G(i,j) only.
+    for (int i = 0; i < d; ++i) {
+      real s = 0;
+      for (int j = 0; j < d; ++j) {
+        real mij = (j <= i) ? M_lower_syrk[(size_t)i * d + j] : (real)(g_scale * G(i, j));
+        s += mij * (real)x[j];
+      }
+      out[i] = (float)((real)x[i] - (real)step * (s - rhs[i]));
+    }
+  }
+
+  // ---- ALS steps --------------------------------------------------------------
+  // IALSRecommender::Step ials.h:317-365.  rows = by_user (solve U from V) or
+  // by_item (solve V from U); `get_row` maps id -> output row.
+  void StepIals(const std::vector<SpVector>& rows, Mat* out, const std::vector<int>* row_map,
+                const Mat& other) const {
+    Mat G = Gramian(other);  // ials.h:321
+    const int num_other = other.rows;
+    ParallelFor((int)rows.size(), [&](int r) {
+      const SpVector& h = rows[r];
+      if (h.empty()) return;
+      float reg = IalsReg((int)h.size(), num_other);
+      ProjectIals(h, other, G, reg, out->row(row_map ? (*row_map)[r] : r));
+    });
+  }
+
+  // SAFER2Recommender::StepU safer2.h:437-490 (erm_mf.h:397-449).
+  // weight_of == nullptr means weight 1 (the evaluation fold-in, safer2.h:252).
+  void StepU(const std::vector<SpVector>& rows, Mat* out, const std::vector<int>* row_map,
+             const Mat& items, const Mat& G, const float* weight_of) const {
+    const int num_items_ = items.rows;
+    ParallelFor((int)rows.size(), [&](int u) {
+      const SpVector& h = rows[u];
+      if (h.empty()) return;
+      float weight = weight_of ? weight_of[u] : 1.0f;
+      float reg = UserReg(num_items_);
+      ProjectU(h, items, G, reg, weight, out->row(row_map ? (*row_map)[u] : u));
+    });
+  }
+
+  // SAFER2Recommender::StepV safer2.h:493-555 (erm_mf.h:451-513).
+  void StepV(const Dataset& data, const Mat& users, Mat* items) const {
+    std::vector<float> norm_dual_weight(num_users);  // z / |hist| (inf/NaN for empty: never read)
+    for (int u = 0; u < num_users; ++u) norm_dual_weight[u] = dual_weight[u] / user_history_size[u];
+    Mat G = Gramian(users, dual_weight.data());      // U^T diag(z) U over ALL rows, safer2.h:504-509
+    const int nu = users.rows;
+    ParallelFor((int)data.by_item.size(), [&](int v) {
+      const SpVector& h = data.by_item[v];
+      if (h.empty()) return;
+      float reg = ItemReg(v, nu);
+      ProjectV(h, users, G, reg, norm_dual_weight.data(), items->row(v));
+    });
+  }
+
+  // CVaRMFRecommender::StepU cvar_mf.h:426-474 with the swapped arguments of
+  // B-4: ProjectU(..., stepsize := z_u, weight := stepsize_).
+  void StepU_CVaR(const Dataset& data) {
+    const int d = cfg.dim;
+    ParallelFor((int)data.by_user.size(), [&](int u) {
+      const SpVector& h = data.by_user[u];
+      if (h.empty()) return;
+      const float stepsize = dual_weight[u];   // B-4
+      const float weight = cfg.stepsize;       // B-4
+      float reg = UserReg(V.rows);
+      std::vector<real> M((size_t)d * d), rhs(d);
+      // cvar_mf.h:98-132: lower SYRK /n, += uw*G (full), *= weight, diag += reg
+      std::fill(M.begin(), M.end(), (real)0);
+      std::fill(rhs.begin(), rhs.end(), (real)0);
+      Accumulate(h, V, 0, d, nullptr, false, nullptr, M.data(), rhs.data());
+      const int n = (int)h.size();
+      for (int i = 0; i < d; ++i)
+        for (int j = 0; j <= i; ++j) {
+          real m = M[(size_t)i * d + j] / (float)n;
+          m += cfg.uobs_weight * item_gramian(i, j);
+          m *= weight;
+          M[(size_t)i * d + j] = m;
+        }
+      for (int i = 0; i < d; ++i) M[(size_t)i * d + i] += reg;
+      const float s = weight / n;
+      for (int i = 0; i < d; ++i) rhs[i] *= s;
+      std::vector<float> x(U.row(u), U.row(u) + d), out(d);
+      // strict upper of the reference matrix = weight*uw*G(i,j)
+      GradStepFullMatrix(M.data(), item_gramian, weight * cfg.uobs_weight, d, rhs.data(), x.data(),
+                         stepsize, out.data());
+      std::copy(out.begin(), out.end(), U.row(u));
+    });
+  }
+
+  // CVaRMFRecommender::StepV cvar_mf.h:476-538, ProjectV cvar_mf.h:136-180.
+  void StepV_CVaR(const Dataset& data, const Mat& users_prev) {
+    const int d = cfg.dim;
+    std::vector<float> norm_dual_weight(num_users);
+    for (int u = 0; u < num_users; ++u) norm_dual_weight[u] = dual_weight[u] / user_history_size[u];
+    Mat G = Gramian(users_prev, dual_weight.data());
+    ParallelFor((int)data.by_item.size(), [&](int v) {
+      const SpVector& h = data.by_item[v];
+      if (h.empty()) return;
+      float reg = ItemReg(v, users_prev.rows);
+      std::vector<real> M((size_t)d * d), rhs(d);
+      BuildItemSystem(h, users_prev, G, reg, norm_dual_weight.data(), M.data(), rhs.data());
+      std::vector<float> x(V.row(v), V.row(v) + d), out(d);
+      GradStepFullMatrix(M.data(), G, cfg.uobs_weight, d, rhs.data(), x.data(), cfg.stepsize,
+                         out.data());
+      std::copy(out.begin(), out.end(), V.row(v));
+    });
+  }
+
+  // ---- block-subspace (++) steps -----------------------------------------------
+  // PredictDataset ialspp.h:469-517 / safer2pp.h:654-702.
+  void PredictDataset(const std::vector<SpVector>& by_user, const Mat& users,
+                      const std::vector<int>* row_map, std::vector<float>* pred) const {
+    ParallelFor((int)by_user.size(), [&](int u) {
+      const SpVector& h = by_user[u];
+      if (h.empty()) return;
+      const float* ue = users.row(row_map ? (*row_map)[u] : u);
+      for (const auto& ir : h) (*pred)[ir.second] = (float)Dot(V.row(ir.first), ue, V.cols);
+    });
+  }
+
+  // One block update of one row; restates
+  //  iALS++  ProjectBlock ialspp.h:85-145          (mode 0)
+  //  SAFER2++ ProjectU    safer2pp.h:97-159        (mode 1, weight = z_u)
+  //  SAFER2++ ProjectV    safer2pp.h:161-216       (mode 2, w_of = z/n; correct tail)
+  // and the prediction refresh that follows in Step* (ialspp.h:399-406,
+  // safer2pp.h:504-508,587-591).
+  void BlockUpdateRow(int mode, const SpVector& h, float* x_full, const Mat& E, int bs, int be,
+                      const Mat& local_gramian, const Mat& local_global_gramian, float reg,
+                      float weight, const float* w_of, std::vector<float>* pred) const {
+    const int bd = be - bs, d = E.cols;
+    std::vector<real> M((size_t)bd * bd, 0), rhs(bd, 0);
+    const int n = (int)h.size();
+    if (mode == 1) {
+      Accumulate(h, E, bs, bd, nullptr, false, pred->data(), M.data(), rhs.data());
+      for (auto& m : M) m /= (float)n;
+      for (int i = 0; i < bd; ++i)
+        for (int j = 0; j < bd; ++j) M[(size_t)i * bd + j] += cfg.uobs_weight * local_gramian(i, j);
+      for (auto& m : M) m *= weight;
+      const float s = weight / n;
+      for (auto& r : rhs) r *= s;
+      for (int i = 0; i < bd; ++i) {  // rhs += uw * G_{B,:} x * weight ; rhs += reg * x_B
+        real g = 0;
+        for (int j = 0; j < d; ++j) g += (real)local_global_gramian(i, j) * (real)x_full[j];
+        rhs[i] += (real)(cfg.uobs_weight * (float)g * weight);
+        rhs[i] += (real)(reg * x_full[bs + i]);
+      }
+      for (int i = 0; i < bd; ++i) M[(size_t)i * bd + i] += reg;
+    } else {
+      for (int i = 0; i < bd; ++i)
+        for (int j = 0; j < bd; ++j) M[(size_t)i * bd + j] = cfg.uobs_weight * local_gramian(i, j);
+      for (int i = 0; i < bd; ++i) M[(size_t)i * bd + i] += reg;
+      Accumulate(h, E, bs, bd, mode == 2 ? w_of : nullptr, false, pred->data(), M.data(),
+                 rhs.data());
+      for (int i = 0; i < bd; ++i) {
+        real g = 0;
+        for (int j = 0; j < d; ++j) g += (real)local_global_gramian(i, j) * (real)x_full[j];
+        rhs[i] += (real)(cfg.uobs_weight * (float)g);
+        rhs[i] += (real)(reg * x_full[bs + i]);
+      }
+    }
+    bool ok = CholeskySolveLower(M.data(), bd, rhs.data());
+    assert(ok); (void)ok;
+    std::vector<float> delta(bd);
+    for (int i = 0; i < bd; ++i) {
+      float nv = x_full[bs + i] - (float)rhs[i];
+      delta[i] = nv - x_full[bs + i];
+      x_full[bs + i] = nv;
+    }
+    for (const auto& ir : h)
+      (*pred)[ir.second] += (float)Dot(delta.data(), E.row(ir.first) + bs, bd);
+  }
+
+  // IALSppRecommender::Step ialspp.h:351-424 and SAFER2pp StepU safer2pp.h:448-524.
+  void StepBlockUserSide(const std::vector<SpVector>& rows, Mat* out,
+                         const std::vector<int>* row_map, const Mat& E, int bs, int be,
+                         std::vector<float>* pred, bool safer, const float* weight_of) const {
+    Mat lg = GramianGeneral(E, bs, be - bs, E, bs, be - bs, nullptr);
+    Mat lgg = GramianGeneral(E, bs, be - bs, E, 0, E.cols, nullptr);
+    const int num_other = E.rows;
+    ParallelFor((int)rows.size(), [&](int r) {
+      const SpVector& h = rows[r];
+      if (h.empty()) return;
+      float* x = out->row(row_map ? (*row_map)[r] : r);
+      if (safer) {
+        float weight = weight_of ? weight_of[r] : 1.0f;
+        BlockUpdateRow(1, h, x, E, bs, be, lg, lgg, UserReg(num_other), weight, nullptr, pred);
+      } else {
+        BlockUpdateRow(0, h, x, E, bs, be, lg, lgg, IalsReg((int)h.size(), num_other), 1.f,
+                       nullptr, pred);
+      }
+    });
+  }
+
+  // SAFER2ppRecommender::StepV safer2pp.h:526-609.
+  void StepBlockV_Safer(const Dataset& data, int bs, int be, std::vector<float>* pred) {
+    std::vector<float> norm_dual_weight(num_users);
+    for (int u = 0; u < num_users; ++u) norm_dual_weight[u] = dual_weight[u] / user_history_size[u];
+    Mat lg = GramianGeneral(U, bs, be - bs, U, bs, be - bs, dual_weight.data());
+    Mat lgg = GramianGeneral(U, bs, be - bs, U, 0, U.cols, dual_weight.data());
+    ParallelFor((int)data.by_item.size(), [&](int v) {
+      const SpVector& h = data.by_item[v];
+      if (h.empty()) return;
+      BlockUpdateRow(2, h, V.row(v), U, bs, be, lg, lgg, ItemReg(v, U.rows), 1.f,
+                     norm_dual_weight.data(), pred);
+    });
+  }
+
+  // ---- xi / dual weights ----------------------------------------------------------
+  // EvaluateQuantile safer2.h:652-689 (safer2pp.h:758-789): value, grad, H.
+  std::tuple<float, float, float> EvaluateQuantile(float xi, const float* loss, int n) const {
+    // Eigen's packet-wise float reduction is not reproducible; the three means are
+    // accumulated in double and rounded to float once.
+    double s_cdf = 0, s_pdf = 0, s_loss = 0;
+    const float h = cfg.bandwidth, alpha = cfg.alpha;
+    for (int i = 0; i < n; ++i) {
+      const float u = loss[i] - xi;  // r = user_loss - xi
+      if (cfg.use_epanechnikov) {
+        s_cdf += epanechnikov_kernel_cdf(-u, h);
+        s_pdf += epanechnikov_kernel(-u, h);
+        s_loss += epanechnikov_loss(u, h, alpha);
+      } else {
+        s_cdf += gaussian_kernel_cdf(-u, h);
+        s_pdf += gaussian_kernel(-u, h);
+        s_loss += gaussian_loss(u, h, alpha);
+      }
+    }
+    float mean_cdf = (float)(s_cdf / n), mean_pdf = (float)(s_pdf / n),
+          mean_loss = (float)(s_loss / n);
+    float grad = (-(1 - alpha) + mean_cdf) / alpha;
+    float H = mean_pdf / alpha;
+    float value = mean_loss / alpha;
+    return {value, grad, H};
+  }
+
+  // ComputeXiDirection safer2.h:692-712 (B-6: the Armijo test uses grad_fx).
+  float ComputeXiDirection(float xi, const float* loss, int n) const {
+    auto [f0, grad_f0, H] = EvaluateQuantile(xi, loss, n);
+    const float d = grad_f0 / H;
+    const float c = 1e-4;
+    float gamma = 1.0;
+    float x = xi + gamma * (-d);
+    for (int k = 0; k < 32; k++) {
+      auto [fx, grad_fx, H_fx] = EvaluateQuantile(x, loss, n);
+      (void)H_fx;
+      if (fx > f0 + c * gamma * grad_fx * (-d)) {
+        gamma *= 0.5;
+        x = xi + gamma * (-d);
+      } else {
+        break;
+      }
+    }
+    return -gamma * d;
+  }
+
+  // The SNR index draw of safer2.h:727-736 with an injected seed.
+  static std::vector<int> DrawSnrIndices(int num_users, float sampling_ratio, unsigned seed) {
+    std::mt19937 rng(seed);
+    std::uniform_int_distribution<int> uni(0, num_users - 1);
+    std::vector<int> sample_inds;
+    int num_samples = num_users * sampling_ratio;  // float product truncated (B-10)
+    for (int j = 0; j < num_samples; j++) sample_inds.push_back(uni(rng));
+    return sample_inds;
+  }
+
+  // ComputeXi safer2.h:716-742.
+  float ComputeXi(const std::vector<float>& loss, float start_xi, int nr_iterations) {
+    const int n = (int)loss.size();
+    float xi = start_xi;
+    last_snr_indices.clear();
+    for (int t = 0; t < nr_iterations; ++t) {
+      float d = 0;
+      if (!cfg.use_snr) {
+        d = ComputeXiDirection(xi, loss.data(), n);
+      } else {
+        unsigned seed = cfg.snr_seed + 1000u * (unsigned)xi_calls + (unsigned)t;
+        std::vector<int> idx = DrawSnrIndices(n, cfg.sampling_ratio, seed);
+        std::vector<float> sub(idx.size());
+        for (size_t j = 0; j < idx.size(); ++j) sub[j] = loss[idx[j]];
+        d = ComputeXiDirection(xi, sub.data(), (int)sub.size());
+        last_snr_indices.push_back(std::move(idx));
+      }
+      xi = xi + d;
+    }
+    ++xi_calls;
+    return xi;
+  }
+
+  // CVaRMFRecommender::ComputeXi cvar_mf.h:582-595: exact order statistic.
+  float ComputeXiExact(const std::vector<float>& loss) const {
+    std::vector<float> vals;
+    vals.reserve(loss.size());
+    for (float l : loss) vals.push_back(-l);
+    auto const Q = vals.size() * cfg.alpha;  // size_t * float -> float
+    std::nth_element(vals.begin(), vals.begin() + (long)Q, vals.end());
+    return -vals[(size_t)(vals.size() * cfg.alpha)];
+  }
+
+  // ComputeUserWeights: safer2.h:745-794 (users with history only),
+  // safer2pp.h:839-862 (all users), cvar_mf.h:597-642 (indicator).
+  void ComputeUserWeights(const Dataset& data, float xi) {
+    for (int u = 0; u < num_users; ++u) {
+      const bool has_hist = u < (int)data.by_user.size() && !data.by_user[u].empty();
+      if (cfg.model != kSAFER2pp && !has_hist) continue;
+      float r = user_loss[u] - xi;
+      float new_weight;
+      if (cfg.model == kCVaRMF)
+        new_weight = (user_loss[u] - xi) >= 0;
+      else if (cfg.use_epanechnikov)
+        new_weight = 1 - epanechnikov_kernel_cdf(-r, cfg.bandwidth);
+      else
+        new_weight = 1 - gaussian_kernel_cdf(-r, cfg.bandwidth);
+      dual_weight[u] = new_weight;
+    }
+  }
+
+  float GetMeanWeight() const {  // safer2.h:815-817
+    double s = 0;
+    for (float z : dual_weight) s += z;
+    return (float)(s / dual_weight.size());
+  }
+  float WeightedLossMean() const {  // safer2.h:300-301
+    double s = 0;
+    for (int u = 0; u < num_users; ++u) s += (double)(dual_weight[u] * user_loss[u]);
+    return (float)(s / num_users);
+  }
+
+  // ---- Initialize -------------------------------------------------------------------
+  // safer2.h:819-838, safer2pp.h Initialize, erm_mf.h:573-587, cvar_mf.h:710-726.
+  void Initialize(const Dataset& data) {
+    if (is_ials_family()) return;  // run_model.cc:246-257 calls it for the other four only
+    std::vector<float> pred;
+    if (cfg.model == kSAFER2pp) {
+      pred.assign(data.num_tuples, 0.f);
+      PredictDataset(data.by_user, U, nullptr, &pred);
+    }
+    ComputeUserLoss(data, item_gramian, cfg.model == kSAFER2pp ? pred.data() : nullptr);
+    if (cfg.model == kSAFER2 || cfg.model == kSAFER2pp) {
+      double s = 0;
+      for (float l : user_loss) s += l;
+      float start = (float)(s / user_loss.size());  // user_loss_.mean()
+      prev_xi = ComputeXi(user_loss, start, cfg.xi_iterations);
+    }
+    // cvar_mf.h:713 computes a local prev_xi and drops it (B-7): prev_xi stays 0.
+    for (size_t u = 0; u < data.by_user.size(); ++u)
+      if (!data.by_user[u].empty()) user_history_size[u] = (float)data.by_user[u].size();
+    for (size_t v = 0; v < data.by_item.size(); ++v)
+      for (auto& ur : data.by_item[v])
+        item_reg[v] += 1.0 / user_history_size[ur.first];  // float += double
+  }
+
+  // ---- loss statistics ------------------------------------------------------------------
+  // PrintLosses safer2.h:337-413 / ComputeLosses ials.h:226-305.  Sums are in
+  // double here (the reference mixes float/double; compare at 1e-3 relative).
+  LossStats ComputeStats(const Dataset& data) const {
+    LossStats s;
+    const int d = cfg.dim;
+    double obs = 0;
+    for (size_t u = 0; u < data.by_user.size(); ++u)
+      for (auto& ir : data.by_user[u]) {
+        double p = (float)Dot(V.row(ir.first), U.row(u), d);
+        obs += (p - 1.0) * (p - 1.0);
+      }
+    double reg = 0, ru = 0, ri = 0;
+    for (size_t u = 0; u < data.by_user.size(); ++u) {
+      if (data.by_user[u].empty()) continue;
+      double n2 = Dot(U.row(u), U.row(u), d);
+      reg += n2 * (is_ials_family() ? IalsReg((int)data.by_user[u].size(), num_items)
+                                    : UserReg(num_items));
+      ru += n2;
+    }
+    for (size_t v = 0; v < data.by_item.size(); ++v) {
+      if (data.by_item[v].empty()) continue;
+      double n2 = Dot(V.row(v), V.row(v), d);
+      reg += n2 * (is_ials_family() ? IalsReg((int)data.by_item[v].size(), num_users)
+                                    : ItemReg((int)v, num_users));
+      ri += n2;
+    }
+    Mat GU = Gramian(U), GV = Gramian(V);
+    double unobs = 0;
+    for (size_t k = 0; k < GU.a.size(); ++k) unobs += (double)GU.a[k] * GV.a[k];
+    s.loss_observed = obs / data.num_tuples;
+    s.loss_unobserved = unobs / num_items / num_users;
+    s.loss_reg = reg;
+    s.loss_reg_user = ru / num_users;
+    s.loss_reg_item = ri / num_items;
+    if (is_ials_family()) {
+      s.loss = obs + cfg.uobs_weight * unobs + reg;  // ials.h:276-278
+    } else {
+      double l = 0;
+      for (float x : user_loss) l += x;  // safer2.h:388 (previous epoch's losses, B-9)
+      s.loss = l;
+    }
+    return s;
+  }
+
+  // ---- Train -------------------------------------------------------------------------------
+  void Train(const Dataset& data) {
+    switch (cfg.model) {
+      case kIALS: TrainIals(data); break;
+      case kIALSpp: TrainIalspp(data); break;
+      case kERMMF: TrainErm(data); break;
+      case kCVaRMF: TrainCvar(data); break;
+      case kSAFER2: TrainSafer2(data); break;
+      case kSAFER2pp: TrainSafer2pp(data); break;
+    }
+  }
+
+  // IALSRecommender::Train ials.h:187-224.
+  void TrainIals(const Dataset& data) {
+    StepIals(data.by_user, &U, nullptr, V);
+    StepIals(data.by_item, &V, nullptr, U);
+    if (print_train_stats) last_stats = ComputeStats(data);
+    Mat G = Gramian(V);  // ComputeUserLoss recomputes it, ials.h:371
+    ComputeUserLoss(data, G, nullptr);
+  }
+
+  // IALSppRecommender::Train ialspp.h:208-261.
+  void TrainIalspp(const Dataset& data) {
+    std::vector<float> pred(data.num_tuples, 0.f);
+    PredictDataset(data.by_user, U, nullptr, &pred);
+    for (int start = 0; start < cfg.dim; start += cfg.block_size) {
+      int end = std::min(start + cfg.block_size, cfg.dim);
+      StepBlockUserSide(data.by_user, &U, nullptr, V, start, end, &pred, false, nullptr);
+      StepBlockUserSide(data.by_item, &V, nullptr, U, start, end, &pred, false, nullptr);
+    }
+    if (print_train_stats) last_stats = ComputeStats(data);
+  }
+
+  // ERMMFRecommender::Train erm_mf.h:257-301.
+  void TrainErm(const Dataset& data) {
+    if (print_train_stats) last_stats = ComputeStats(data);
+    StepU(data.by_user, &U, nullptr, V, item_gramian, dual_weight.data());
+    StepV(data, U, &V);
+    item_gramian = Gramian(V);
+    ComputeUserLoss(data, item_gramian, nullptr);
+    last_weighted_loss = WeightedLossMean();
+  }
+
+  // CVaRMFRecommender::Train cvar_mf.h:276-330.
+  void TrainCvar(const Dataset& data) {
+    if (print_train_stats) last_stats = ComputeStats(data);
+    ComputeUserWeights(data, prev_xi);
+    Mat U_prev = U;  // cvar_mf.h:282
+    StepU_CVaR(data);
+    StepV_CVaR(data, U_prev);
+    item_gramian = Gramian(V);
+    ComputeUserLoss(data, item_gramian, nullptr);
+    last_weighted_loss = WeightedLossMean();
+    prev_xi = ComputeXiExact(user_loss);
+  }
+
+  // SAFER2Recommender::Train safer2.h:266-334.
+  void TrainSafer2(const Dataset& data) {
+    if (print_train_stats) last_stats = ComputeStats(data);
+    for (int t = 0; t < cfg.pd_iterations; ++t) {
+      ComputeUserWeights(data, prev_xi);
+      StepU(data.by_user, &U, nullptr, V, item_gramian, dual_weight.data());
+      StepV(data, U, &V);
+      item_gramian = Gramian(V);
+      ComputeUserLoss(data, item_gramian, nullptr);
+      last_weighted_loss = WeightedLossMean();
+    }
+    prev_xi = ComputeXi(user_loss, prev_xi, cfg.xi_iterations);
+  }
+
+  // SAFER2ppRecommender::Train safer2pp.h:288-355.
+  void TrainSafer2pp(const Dataset& data) {
+    if (print_train_stats) last_stats = ComputeStats(data);
+    std::vector<float> pred(data.num_tuples, 0.f);
+    PredictDataset(data.by_user, U, nullptr, &pred);
+    for (int t = 0; t < cfg.pd_iterations; ++t) {
+      ComputeUserWeights(data, prev_xi);
+      for (int start = 0; start < cfg.dim; start += cfg.block_size) {
+        int end = std::min(start + cfg.block_size, cfg.dim);
+        StepBlockUserSide(data.by_user, &U, nullptr, V, start, end, &pred, true,
+                          dual_weight.data());
+        StepBlockV_Safer(data, start, end, &pred);
+      }
+      item_gramian = Gramian(V);
+      ComputeUserLoss(data, item_gramian, pred.data());
+      last_weighted_loss = WeightedLossMean();
+    }
+    prev_xi = ComputeXi(user_loss, prev_xi, cfg.xi_iterations);
+  }
+
+  // ---- EvaluateDataset --------------------------------------------------------------------------
+  // Fold-in + ranking metrics: safer2.h:225-263, ials.h:148-185,
+  // ialspp.h:149-206 (8 block-sweep epochs), safer2pp.h:220-286,
+  // erm_mf.h:212-255, cvar_mf.h:232-274; then recommender.h:78-129.
+  // Result rows follow ascending user id of `test_tr` (the reference uses hash
+  // iteration order; only the row order differs).
+  EvalResult Evaluate(const Dataset& test_tr, const Dataset& test_te,
+                      const std::vector<int>& k_list, bool want_topk, Mat* folded_out = nullptr) {
+    EvalResult res;
+    res.k_list = k_list;
+    std::vector<int> row_map(test_tr.by_user.size(), -1);
+    for (size_t u = 0; u < test_tr.by_user.size(); ++u)
+      if (!test_tr.by_user[u].empty()) {
+        row_map[u] = (int)res.user_ids.size();
+        res.user_ids.push_back((int)u);
+      }
+    const int nu = (int)res.user_ids.size();
+    Mat UE(nu, cfg.dim);  // MatrixXf::Zero
+    switch (cfg.model) {
+      case kIALS:
+        StepIals(test_tr.by_user, &UE, &row_map, V);
+        break;
+      case kERMMF:
+      case kCVaRMF:
+      case kSAFER2:
+        StepU(test_tr.by_user, &UE, &row_map, V, item_gramian, nullptr);
+        break;
+      case kIALSpp:
+      case kSAFER2pp: {
+        std::vector<float> pred(test_tr.num_tuples, 0.f);
+        for (int e = 0; e < 8; ++e) {
+          PredictDataset(test_tr.by_user, UE, &row_map, &pred);
+          for (int start = 0; start < cfg.dim; start += cfg.block_size) {
+            int end = std::min(start + cfg.block_size, cfg.dim);
+            StepBlockUserSide(test_tr.by_user, &UE, &row_map, V, start, end, &pred,
+                              cfg.model == kSAFER2pp, nullptr);
+          }
+        }
+        break;
+      }
+    }
+    if (folded_out) *folded_out = UE;
+    const int nk = (int)k_list.size();
+    res.max_k = *std::max_element(k_list.begin(), k_list.end());
+    res.recall = Mat(nu, nk);
+    res.ndcg = Mat(nu, nk);
+    if (want_topk) res.topk.assign((size_t)nu * res.max_k, -1);
+    ParallelFor((int)test_te.by_user.size(), [&](int u) {
+      const SpVector& gt = test_te.by_user[u];
+      if (gt.empty()) return;
+      const int r = row_map[u];
+      const SpVector& hist = test_tr.by_user[u];
+      std::vector<float> scores(num_items);
+      for (int i = 0; i < num_items; ++i) scores[i] = (float)Dot(V.row(i), UE.row(r), cfg.dim);
+      EvaluateUser(k_list, std::move(scores), gt, hist, res.recall.row(r), res.ndcg.row(r),
+                   want_topk ? res.topk.data() + (size_t)r * res.max_k : nullptr);
+    });
+    return res;
+  }
+};
+
+// EvaluationResult::cvar evaluation.h:83-102 (lower-tail CVaR of one metric
+// column at each alpha).
+inline std::vector<float> MetricCVaR(std::vector<float> ms, const std::vector<float>& alpha_list) {
+  std::sort(ms.begin(), ms.end());
+  int counter = 0;
+  std::vector<float> cvars(alpha_list.size(), 0.f);
+  float accs = 0;
+  for (size_t i = 0; i < ms.size(); i++) {
+    accs += ms[i];
+    for (size_t j = counter; j < alpha_list.size(); j++) {
+      int pos = ms.size() * alpha_list[j];
+      if (pos == (int)i) {
+        cvars[counter] = accs / (i + 1);
+        counter++;
+      }
+    }
+  }
+  return cvars;
+}
+
+}  // namespace oracle
