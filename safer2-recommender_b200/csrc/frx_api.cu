@@ -1,0 +1,1054 @@
+// C ABI (include/frecsys_b200.h) and the host-side sequencing of the epoch
+// stages.  Each frx_model_* entry point restates the stage ORDER of the
+// reference method it replaces (cited inline); the arithmetic is in the kernels.
+#include "../../include/frecsys_b200.h"
+#include "frx_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#ifdef FRX_WITH_NCCL
+#include <nccl.h>
+#endif
+
+using namespace frx;
+
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(FRX_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+struct StageTimer {
+  std::string name;
+  cudaEvent_t a, b;
+};
+
+struct frx_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int num_sms = 148;
+  long long launches = 0;
+  float* gram_ws = nullptr;
+  size_t gram_ws_floats = 0;
+  float* row_scratch = nullptr;
+  size_t row_scratch_floats = 0;
+  double* dws = nullptr;   // xi partials / mean partials
+  int* status_dev = nullptr;
+  bool profiling = false;
+  std::vector<StageTimer> timers;
+  size_t timers_used = 0;
+  int rank = 0, world = 1;
+#ifdef FRX_WITH_NCCL
+  ncclComm_t comm = nullptr;
+#endif
+  int ensure_gram_ws(size_t floats) {
+    if (floats <= gram_ws_floats) return 0;
+    if (gram_ws) cudaFree(gram_ws);
+    gram_ws = nullptr;
+    gram_ws_floats = 0;
+    CK(cudaMalloc(&gram_ws, floats * sizeof(float)));
+    gram_ws_floats = floats;
+    return 0;
+  }
+  int ensure_row_scratch(size_t floats) {
+    if (floats <= row_scratch_floats) return 0;
+    if (row_scratch) cudaFree(row_scratch);
+    row_scratch = nullptr;
+    row_scratch_floats = 0;
+    CK(cudaMalloc(&row_scratch, floats * sizeof(float)));
+    row_scratch_floats = floats;
+    return 0;
+  }
+  void stage_begin(const char* name) {
+    if (!profiling) return;
+    if (timers_used == timers.size()) {
+      StageTimer t;
+      cudaEventCreate(&t.a);
+      cudaEventCreate(&t.b);
+      timers.push_back(t);
+    }
+    timers[timers_used].name = name;
+    cudaEventRecord(timers[timers_used].a, stream);
+  }
+  void stage_end() {
+    if (!profiling) return;
+    cudaEventRecord(timers[timers_used].b, stream);
+    ++timers_used;
+  }
+};
+
+struct Csr {
+  int nrows = 0;
+  int* ptr = nullptr;
+  int* col = nullptr;
+  int* tup = nullptr;
+  int* order = nullptr;  // this rank's non-empty rows, longest first
+  int num_order = 0;
+  int distinct = 0;
+  std::vector<int> h_ptr;
+  std::vector<int> rank_begin;  // row-id range per rank [world+1]
+};
+
+struct frx_dataset {
+  frx_context* ctx = nullptr;
+  int num_tuples = 0, max_user = -1, max_item = -1;
+  Csr by_user, by_item;
+  // evaluation helpers (built lazily): ascending ids of non-empty users and id -> compact row
+  std::vector<int> h_user_ids;
+  int* xmap = nullptr;
+  int* user_ids_dev = nullptr;
+};
+
+struct frx_model {
+  frx_context* ctx = nullptr;
+  frx_config cfg;
+  int num_users = 0, num_items = 0;
+  float *U = nullptr, *V = nullptr, *G = nullptr, *Gz = nullptr;
+  float *z = nullptr, *loss = nullptr, *hist_size = nullptr, *item_reg = nullptr, *norm_w = nullptr,
+        *quad = nullptr, *Uprev = nullptr, *pred = nullptr;
+  size_t pred_cap = 0;
+  float* scal = nullptr;  // device: [0]=prev_xi [1]=mean z [2]=mean z*loss
+  int xi_calls = 0;
+  std::vector<std::vector<int>> last_snr;
+  int* snr_dev = nullptr;
+  size_t snr_cap = 0;
+  int* snr_host[2] = {nullptr, nullptr};
+  size_t snr_host_cap[2] = {0, 0};
+  cudaEvent_t snr_ev[2] = {nullptr, nullptr};
+  int snr_slot = 0;
+  bool is_pp() const { return cfg.model == FRX_IALSPP || cfg.model == FRX_SAFER2PP; }
+  bool is_ials_family() const { return cfg.model == FRX_IALS || cfg.model == FRX_IALSPP; }
+};
+
+extern "C" const char* frx_last_error(void) { return g_err.c_str(); }
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+extern "C" int frx_context_create(int device, void* cuda_stream, frx_context** out) {
+  if (!out) return fail(FRX_ERR_ARG, "out is null");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(FRX_ERR_CUDA, "no CUDA device (%s): frecsys_b200 has no CPU fallback",
+                cudaGetErrorString(e));
+  CK(cudaSetDevice(device));
+  frx_context* c = new frx_context();
+  c->device = device;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  c->num_sms = prop.multiProcessorCount;
+  if (cuda_stream) {
+    c->stream = (cudaStream_t)cuda_stream;
+  } else {
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
+  CK(cudaMalloc(&c->dws, sizeof(double) * (xi_partials_doubles(c->num_sms) + 512)));
+  CK(cudaMalloc(&c->status_dev, sizeof(int)));
+  CK(cudaMemset(c->status_dev, 0, sizeof(int)));
+  *out = c;
+  return FRX_OK;
+}
+
+extern "C" void frx_context_destroy(frx_context* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+#ifdef FRX_WITH_NCCL
+  if (c->comm) ncclCommDestroy(c->comm);
+#endif
+  for (auto& t : c->timers) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+  cudaFree(c->gram_ws);
+  cudaFree(c->row_scratch);
+  cudaFree(c->dws);
+  cudaFree(c->status_dev);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" int frx_context_sync(frx_context* c) {
+  CK(cudaStreamSynchronize(c->stream));
+  int st = 0;
+  CK(cudaMemcpy(&st, c->status_dev, sizeof(int), cudaMemcpyDeviceToHost));
+  if (st != 0) {
+    cudaMemset(c->status_dev, 0, sizeof(int));
+    return fail(FRX_ERR_NUMERIC, "non-positive Cholesky pivot (reference asserts at safer2.h:160)");
+  }
+  return FRX_OK;
+}
+extern "C" void* frx_context_stream(frx_context* c) { return (void*)c->stream; }
+extern "C" long long frx_context_launch_count(frx_context* c) { return c->launches; }
+extern "C" int frx_context_set_profiling(frx_context* c, int on) {
+  c->profiling = on != 0;
+  c->timers_used = 0;
+  return FRX_OK;
+}
+extern "C" int frx_context_stage_times(frx_context* c, char* names_buf, int buf_len, float* ms, int max_n) {
+  CK(cudaStreamSynchronize(c->stream));
+  std::string names;
+  int n = 0;
+  for (size_t i = 0; i < c->timers_used && n < max_n; ++i, ++n) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, c->timers[i].a, c->timers[i].b);
+    ms[n] = t;
+    if (i) names += ";";
+    names += c->timers[i].name;
+  }
+  if (names_buf && buf_len > 0) {
+    strncpy(names_buf, names.c_str(), buf_len - 1);
+    names_buf[buf_len - 1] = 0;
+  }
+  return n;
+}
+
+extern "C" int frx_comm_unique_id(void* out128) {
+#ifdef FRX_WITH_NCCL
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return fail(FRX_ERR_COMM, "ncclGetUniqueId failed");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(out128, &id, 128);
+  return FRX_OK;
+#else
+  (void)out128;
+  return fail(FRX_ERR_COMM, "built without NCCL");
+#endif
+}
+extern "C" int frx_context_init_comm(frx_context* c, int rank, int world, const void* id128) {
+  if (world <= 1) { c->rank = 0; c->world = 1; return FRX_OK; }
+#ifdef FRX_WITH_NCCL
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  CK(cudaSetDevice(c->device));
+  ncclResult_t r = ncclCommInitRank(&c->comm, world, id, rank);
+  if (r != ncclSuccess) return fail(FRX_ERR_COMM, "ncclCommInitRank: %s", ncclGetErrorString(r));
+  c->rank = rank;
+  c->world = world;
+  return FRX_OK;
+#else
+  (void)rank; (void)id128;
+  return fail(FRX_ERR_COMM, "built without NCCL");
+#endif
+}
+
+// ---------------------------------------------------------------------------
+// dataset
+// ---------------------------------------------------------------------------
+static int finish_csr(frx_context* c, Csr& m, const int* cost_other_dim) {
+  (void)cost_other_dim;
+  m.h_ptr.resize(m.nrows + 1);
+  CK(cudaMemcpyAsync(m.h_ptr.data(), m.ptr, sizeof(int) * (m.nrows + 1), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  // Row-id ranges per rank, balanced on history length; rank k owns [rank_begin[k], rank_begin[k+1]).
+  m.rank_begin.assign(c->world + 1, m.nrows);
+  m.rank_begin[0] = 0;
+  {
+    const long long total = m.h_ptr[m.nrows] + (long long)m.nrows;  // nnz + one unit per row
+    int k = 1;
+    for (int r = 0; r < m.nrows && k < c->world; ++r) {
+      const long long done = m.h_ptr[r + 1] + (long long)(r + 1);
+      while (k < c->world && done >= total * k / c->world) m.rank_begin[k++] = r + 1;
+    }
+    for (; k < c->world; ++k) m.rank_begin[k] = m.nrows;
+  }
+  std::vector<int> order;
+  m.distinct = 0;
+  for (int r = 0; r < m.nrows; ++r)
+    if (m.h_ptr[r + 1] > m.h_ptr[r]) ++m.distinct;
+  for (int r = m.rank_begin[c->rank]; r < m.rank_begin[c->rank + 1]; ++r)
+    if (m.h_ptr[r + 1] > m.h_ptr[r]) order.push_back(r);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    return (m.h_ptr[a + 1] - m.h_ptr[a]) > (m.h_ptr[b + 1] - m.h_ptr[b]);
+  });
+  m.num_order = (int)order.size();
+  CK(cudaMalloc(&m.order, sizeof(int) * (size_t)std::max(1, m.num_order)));
+  if (m.num_order)
+    CK(cudaMemcpy(m.order, order.data(), sizeof(int) * (size_t)m.num_order, cudaMemcpyHostToDevice));
+  return FRX_OK;
+}
+
+extern "C" int frx_dataset_create(frx_context* c, int n, const int* users, const int* items,
+                                  frx_dataset** out) {
+  if (!c || !out || n < 0 || (n > 0 && (!users || !items))) return fail(FRX_ERR_ARG, "bad dataset arguments");
+  CK(cudaSetDevice(c->device));
+  frx_dataset* d = new frx_dataset();
+  d->ctx = c;
+  d->num_tuples = n;
+  for (int t = 0; t < n; ++t) {  // dataset.h:90-91
+    if (users[t] < 0 || items[t] < 0) { delete d; return fail(FRX_ERR_ARG, "negative id at tuple %d", t); }
+    d->max_user = std::max(d->max_user, users[t]);
+    d->max_item = std::max(d->max_item, items[t]);
+  }
+  int *du = nullptr, *di = nullptr;
+  const size_t nb = sizeof(int) * (size_t)std::max(1, n);
+  CK(cudaMalloc(&du, nb));
+  CK(cudaMalloc(&di, nb));
+  if (n) {
+    CK(cudaMemcpyAsync(du, users, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(di, items, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  }
+  Csr* sides[2] = {&d->by_user, &d->by_item};
+  for (int sd = 0; sd < 2; ++sd) {
+    Csr& m = *sides[sd];
+    m.nrows = (sd == 0 ? d->max_user : d->max_item) + 1;
+    CK(cudaMalloc(&m.ptr, sizeof(int) * (size_t)(m.nrows + 1)));
+    CK(cudaMalloc(&m.col, nb));
+    CK(cudaMalloc(&m.tup, nb));
+    build_csr(sd == 0 ? du : di, sd == 0 ? di : du, n, m.nrows, m.ptr, m.col, m.tup, c->stream, &c->launches);
+    CK(cudaGetLastError());
+    int rc = finish_csr(c, m, nullptr);
+    if (rc) return rc;
+  }
+  CK(cudaFree(du));
+  CK(cudaFree(di));
+  *out = d;
+  return FRX_OK;
+}
+
+extern "C" void frx_dataset_destroy(frx_dataset* d) {
+  if (!d) return;
+  cudaSetDevice(d->ctx->device);
+  cudaStreamSynchronize(d->ctx->stream);
+  for (Csr* m : {&d->by_user, &d->by_item}) {
+    cudaFree(m->ptr); cudaFree(m->col); cudaFree(m->tup); cudaFree(m->order);
+  }
+  cudaFree(d->xmap);
+  cudaFree(d->user_ids_dev);
+  delete d;
+}
+
+extern "C" int frx_dataset_info(frx_dataset* d, int* out5) {
+  out5[0] = d->max_user; out5[1] = d->max_item; out5[2] = d->num_tuples;
+  out5[3] = d->by_user.distinct; out5[4] = d->by_item.distinct;
+  return FRX_OK;
+}
+
+extern "C" int frx_dataset_get_csr(frx_dataset* d, int by_item, int nrows, int* ptr, int* ids, int* tup) {
+  Csr& m = by_item ? d->by_item : d->by_user;
+  CK(cudaStreamSynchronize(d->ctx->stream));
+  for (int r = 0; r <= nrows; ++r) ptr[r] = m.h_ptr[std::min(r, m.nrows)];
+  if (d->num_tuples) {
+    CK(cudaMemcpy(ids, m.col, sizeof(int) * (size_t)d->num_tuples, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(tup, m.tup, sizeof(int) * (size_t)d->num_tuples, cudaMemcpyDeviceToHost));
+  }
+  return FRX_OK;
+}
+
+static int ensure_eval_maps(frx_dataset* d) {
+  if (d->xmap) return FRX_OK;
+  Csr& m = d->by_user;
+  std::vector<int> xmap(std::max(1, m.nrows), -1);
+  for (int r = 0; r < m.nrows; ++r)
+    if (m.h_ptr[r + 1] > m.h_ptr[r]) {
+      xmap[r] = (int)d->h_user_ids.size();
+      d->h_user_ids.push_back(r);
+    }
+  CK(cudaMalloc(&d->xmap, sizeof(int) * xmap.size()));
+  CK(cudaMemcpy(d->xmap, xmap.data(), sizeof(int) * xmap.size(), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&d->user_ids_dev, sizeof(int) * std::max<size_t>(1, d->h_user_ids.size())));
+  if (!d->h_user_ids.empty())
+    CK(cudaMemcpy(d->user_ids_dev, d->h_user_ids.data(), sizeof(int) * d->h_user_ids.size(), cudaMemcpyHostToDevice));
+  return FRX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// model
+// ---------------------------------------------------------------------------
+static int gramian_into(frx_model* m, const float* E, int n, int cs, int bd, int fs, int fd,
+                        const float* w, float* out) {
+  frx_context* c = m->ctx;
+  const int d = m->cfg.dim;
+  int rc = c->ensure_gram_ws(gramian_workspace_floats(n, bd, fd, c->num_sms));
+  if (rc) return rc;
+  launch_gramian(E, n, d, cs, bd, fs, fd, w, out + (size_t)cs * d + fs, d, c->gram_ws, c->gram_ws_floats,
+                 c->stream, c->num_sms, &c->launches);
+  CK(cudaGetLastError());
+  return FRX_OK;
+}
+
+static int reset_state(frx_model* m) {
+  // constructor tail: safer2.h:55-59 — G_V = V^T V, z = alpha, loss = 0, hist = 0, item_reg = 0, xi = 0
+  frx_context* c = m->ctx;
+  int rc = gramian_into(m, m->V, m->num_items, 0, m->cfg.dim, 0, m->cfg.dim, nullptr, m->G);
+  if (rc) return rc;
+  launch_fill(m->z, m->num_users, m->cfg.alpha, c->stream, &c->launches);
+  CK(cudaMemsetAsync(m->loss, 0, sizeof(float) * m->num_users, c->stream));
+  CK(cudaMemsetAsync(m->hist_size, 0, sizeof(float) * m->num_users, c->stream));
+  CK(cudaMemsetAsync(m->item_reg, 0, sizeof(float) * m->num_items, c->stream));
+  CK(cudaMemsetAsync(m->scal, 0, sizeof(float) * 4, c->stream));
+  m->xi_calls = 0;
+  return FRX_OK;
+}
+
+extern "C" int frx_model_create(frx_context* c, const frx_config* cfg, int num_users, int num_items,
+                                frx_model** out) {
+  if (!c || !cfg || !out || num_users <= 0 || num_items <= 0 || cfg->dim <= 0 || cfg->dim > 1024)
+    return fail(FRX_ERR_ARG, "bad model arguments (dim must be in [1,1024])");
+  if (cfg->model < 0 || cfg->model > FRX_SAFER2PP) return fail(FRX_ERR_ARG, "unknown model kind %d", cfg->model);
+  CK(cudaSetDevice(c->device));
+  frx_model* m = new frx_model();
+  m->ctx = c;
+  m->cfg = *cfg;
+  if (m->cfg.block_size <= 0) m->cfg.block_size = 64;
+  m->num_users = num_users;
+  m->num_items = num_items;
+  const size_t d = cfg->dim;
+  CK(cudaMalloc(&m->U, sizeof(float) * num_users * d));
+  CK(cudaMalloc(&m->V, sizeof(float) * num_items * d));
+  CK(cudaMalloc(&m->G, sizeof(float) * d * d));
+  CK(cudaMalloc(&m->Gz, sizeof(float) * d * d));
+  CK(cudaMalloc(&m->z, sizeof(float) * num_users));
+  CK(cudaMalloc(&m->loss, sizeof(float) * num_users));
+  CK(cudaMalloc(&m->hist_size, sizeof(float) * num_users));
+  CK(cudaMalloc(&m->norm_w, sizeof(float) * num_users));
+  CK(cudaMalloc(&m->quad, sizeof(float) * num_users));
+  CK(cudaMalloc(&m->item_reg, sizeof(float) * num_items));
+  CK(cudaMalloc(&m->scal, sizeof(float) * 4));
+  if (cfg->model == FRX_CVAR_MF) CK(cudaMalloc(&m->Uprev, sizeof(float) * num_users * d));
+  CK(cudaMemsetAsync(m->U, 0, sizeof(float) * num_users * d, c->stream));
+  CK(cudaMemsetAsync(m->V, 0, sizeof(float) * num_items * d, c->stream));
+  for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&m->snr_ev[i], cudaEventDisableTiming));
+  int rc = reset_state(m);
+  if (rc) return rc;
+  *out = m;
+  return FRX_OK;
+}
+
+extern "C" void frx_model_destroy(frx_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  for (float* p : {m->U, m->V, m->G, m->Gz, m->z, m->loss, m->hist_size, m->norm_w, m->quad, m->item_reg,
+                   m->scal, m->Uprev, m->pred})
+    cudaFree(p);
+  cudaFree(m->snr_dev);
+  for (int i = 0; i < 2; ++i) {
+    if (m->snr_host[i]) cudaFreeHost(m->snr_host[i]);
+    if (m->snr_ev[i]) cudaEventDestroy(m->snr_ev[i]);
+  }
+  delete m;
+}
+
+extern "C" int frx_model_set_factors(frx_model* m, const float* U, const float* V) {
+  frx_context* c = m->ctx;
+  const size_t d = m->cfg.dim;
+  if (U) CK(cudaMemcpyAsync(m->U, U, sizeof(float) * m->num_users * d, cudaMemcpyHostToDevice, c->stream));
+  if (V) CK(cudaMemcpyAsync(m->V, V, sizeof(float) * m->num_items * d, cudaMemcpyHostToDevice, c->stream));
+  return reset_state(m);
+}
+
+extern "C" int frx_model_init_factors(frx_model* m, unsigned seed) {
+  // Recommender::init_matrix, recommender.h:61-67; order U then V, safer2.h:50-54.
+  const size_t d = m->cfg.dim;
+  std::vector<float> U((size_t)m->num_users * d), V((size_t)m->num_items * d);
+  const float adjusted_stdev = m->cfg.stdev / std::sqrt((double)m->cfg.dim);
+  std::mt19937 gen{seed};
+  {
+    std::normal_distribution<float> dist(0, adjusted_stdev);
+    for (auto& x : U) x = dist(gen);
+  }
+  {
+    std::normal_distribution<float> dist(0, adjusted_stdev);
+    for (auto& x : V) x = dist(gen);
+  }
+  int rc = frx_model_set_factors(m, U.data(), V.data());
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(m->ctx->stream));  // host vectors go out of scope
+  return FRX_OK;
+}
+
+extern "C" int frx_model_get_factors(frx_model* m, float* U, float* V) {
+  frx_context* c = m->ctx;
+  const size_t d = m->cfg.dim;
+  if (U) CK(cudaMemcpyAsync(U, m->U, sizeof(float) * m->num_users * d, cudaMemcpyDeviceToHost, c->stream));
+  if (V) CK(cudaMemcpyAsync(V, m->V, sizeof(float) * m->num_items * d, cudaMemcpyDeviceToHost, c->stream));
+  return frx_context_sync(c);
+}
+
+static int ensure_pred(frx_model* m, size_t n) {
+  if (n <= m->pred_cap) return FRX_OK;
+  if (m->pred) cudaFree(m->pred);
+  m->pred = nullptr;
+  m->pred_cap = 0;
+  CK(cudaMalloc(&m->pred, sizeof(float) * std::max<size_t>(1, n)));
+  m->pred_cap = n;
+  return FRX_OK;
+}
+
+// ---- stage helpers -----------------------------------------------------------------
+struct RowCall {
+  const Csr* rows;
+  const float* E;
+  int num_other;
+  float* X;
+  const float* Xread;
+  const int* xmap;
+  const float* G;
+  const float* entry_w;
+  const float* row_w;
+  int mode;
+  int cs, bd;
+  float* pred;
+};
+
+static int run_rows(frx_model* m, const RowCall& rc_) {
+  frx_context* c = m->ctx;
+  RowParams p;
+  memset(&p, 0, sizeof p);
+  p.ptr = rc_.rows->ptr; p.col = rc_.rows->col; p.tup = rc_.rows->tup;
+  p.order = rc_.rows->order; p.num_rows = rc_.rows->num_order;
+  p.E = rc_.E; p.d = m->cfg.dim; p.num_other = rc_.num_other;
+  p.cs = rc_.cs; p.bd = rc_.bd;
+  p.X = rc_.X; p.Xread = rc_.Xread ? rc_.Xread : rc_.X; p.xmap = rc_.xmap;
+  p.G = rc_.G; p.entry_w = rc_.entry_w; p.row_w = rc_.row_w; p.item_reg = m->item_reg;
+  p.pred = rc_.pred; p.mode = rc_.mode;
+  p.uw = m->cfg.uobs_weight; p.reg = m->cfg.reg; p.reg_exp = m->cfg.reg_exp; p.alpha = m->cfg.alpha;
+  p.stepsize = m->cfg.stepsize; p.num_users_total = m->num_users;
+  p.status = c->status_dev;
+  const size_t per = row_solve_generic_scratch_floats(p.bd);
+  if (per) {
+    const int g = row_solve_generic_grid(p.num_rows, c->num_sms);
+    int r = c->ensure_row_scratch(per * (size_t)g);
+    if (r) return r;
+    p.scratch = c->row_scratch;
+    p.scratch_stride = per;
+  }
+  launch_row_solve_generic(p, c->stream, c->num_sms, &c->launches);
+  CK(cudaGetLastError());
+  return FRX_OK;
+}
+
+static int stage_item_gramian(frx_model* m) {
+  m->ctx->stage_begin("gramian_V");
+  int rc = gramian_into(m, m->V, m->num_items, 0, m->cfg.dim, 0, m->cfg.dim, nullptr, m->G);
+  m->ctx->stage_end();
+  return rc;
+}
+
+static int stage_user_loss(frx_model* m, frx_dataset* ds, const float* G, const float* pred) {
+  frx_context* c = m->ctx;
+  c->stage_begin("user_loss");
+  LossParams p;
+  memset(&p, 0, sizeof p);
+  p.ptr = ds->by_user.ptr; p.col = ds->by_user.col; p.tup = ds->by_user.tup;
+  p.order = ds->by_user.order; p.num_rows = ds->by_user.num_order;
+  p.U = m->U; p.V = m->V; p.d = m->cfg.dim; p.G = G; p.pred = pred;
+  p.beta = m->cfg.uobs_weight; p.halve = m->is_ials_family() ? 0 : 1;
+  p.quad = m->quad; p.loss = m->loss;
+  launch_user_loss(p, m->num_users, c->stream, c->num_sms, &c->launches);
+  c->stage_end();
+  CK(cudaGetLastError());
+  return FRX_OK;
+}
+
+static int stage_weights(frx_model* m) {
+  frx_context* c = m->ctx;
+  c->stage_begin("weights");
+  const int kind = m->cfg.model == FRX_CVAR_MF ? 2 : (m->cfg.use_epanechnikov ? 1 : 0);
+  // safer2.h iterates data.by_user() (users with history); safer2pp.h:847-856 updates all users.
+  const int only_hist = m->cfg.model == FRX_SAFER2PP ? 0 : 1;
+  launch_user_weights(m->loss, m->hist_size, m->num_users, m->z, m->scal, m->cfg.bandwidth, kind, only_hist,
+                      c->stream, &c->launches);
+  c->stage_end();
+  CK(cudaGetLastError());
+  return FRX_OK;
+}
+
+static int stage_means(frx_model* m) {
+  frx_context* c = m->ctx;
+  launch_weight_means(m->z, m->loss, m->num_users, m->scal + 1, c->dws + xi_partials_doubles(c->num_sms),
+                      c->stream, &c->launches);
+  CK(cudaGetLastError());
+  return FRX_OK;
+}
+
+// ComputeXi, safer2.h:716-742.  SNR indices are drawn on the host with the
+// std:: classes of safer2.h:728-736 (bit-exact by construction) and uploaded.
+static int stage_xi(frx_model* m, bool from_mean) {
+  frx_context* c = m->ctx;
+  c->stage_begin("xi");
+  XiParams p;
+  memset(&p, 0, sizeof p);
+  p.loss = m->loss; p.num_users = m->num_users; p.iters = m->cfg.xi_iterations;
+  p.alpha = m->cfg.alpha; p.bandwidth = m->cfg.bandwidth; p.epanechnikov = m->cfg.use_epanechnikov;
+  p.start_from_mean = from_mean ? 1 : 0;
+  p.xi_io = m->scal; p.partials = c->dws;
+  m->last_snr.clear();
+  if (m->cfg.use_snr) {
+    const int num_samples = (int)((float)m->num_users * m->cfg.sampling_ratio);  // B-10
+    const size_t total = (size_t)num_samples * (size_t)std::max(0, p.iters);
+    const int slot = m->snr_slot;
+    m->snr_slot ^= 1;
+    if (total > m->snr_host_cap[slot]) {
+      if (m->snr_host[slot]) cudaFreeHost(m->snr_host[slot]);
+      CK(cudaMallocHost(&m->snr_host[slot], sizeof(int) * total));
+      m->snr_host_cap[slot] = total;
+    } else {
+      CK(cudaEventSynchronize(m->snr_ev[slot]));  // previous upload from this pinned buffer is done
+    }
+    if (total > m->snr_cap) {
+      CK(cudaStreamSynchronize(c->stream));
+      if (m->snr_dev) cudaFree(m->snr_dev);
+      CK(cudaMalloc(&m->snr_dev, sizeof(int) * total));
+      m->snr_cap = total;
+    }
+    for (int t = 0; t < p.iters; ++t) {
+      std::mt19937 rng(m->cfg.snr_seed + 1000u * (unsigned)m->xi_calls + (unsigned)t);
+      std::uniform_int_distribution<int> uni(0, m->num_users - 1);
+      int* dst = m->snr_host[slot] + (size_t)t * num_samples;
+      for (int j = 0; j < num_samples; j++) dst[j] = uni(rng);
+      m->last_snr.emplace_back(dst, dst + num_samples);
+    }
+    if (total) {
+      CK(cudaMemcpyAsync(m->snr_dev, m->snr_host[slot], sizeof(int) * total, cudaMemcpyHostToDevice, c->stream));
+      CK(cudaEventRecord(m->snr_ev[slot], c->stream));
+    }
+    p.snr_idx = m->snr_dev;
+    p.n_samples = num_samples;
+  }
+  ++m->xi_calls;
+  if (launch_xi_newton(p, c->stream, c->num_sms, &c->launches) != 0)
+    return fail(FRX_ERR_CUDA, "cooperative launch of xi_newton_kernel failed: %s",
+                cudaGetErrorString(cudaGetLastError()));
+  c->stage_end();
+  return FRX_OK;
+}
+
+static int stage_xi_exact(frx_model* m) {
+  frx_context* c = m->ctx;
+  c->stage_begin("xi_exact");
+  launch_exact_quantile(m->loss, m->num_users, m->cfg.alpha, m->scal, nullptr, c->stream, &c->launches);
+  c->stage_end();
+  CK(cudaGetLastError());
+  return FRX_OK;
+}
+
+// StepU of SAFER2 / ERM-MF (safer2.h:437-490) on the model's own users.
+static int stage_step_u(frx_model* m, frx_dataset* ds) {
+  m->ctx->stage_begin("step_U");
+  RowCall rc{&ds->by_user, m->V, m->num_items, m->U, nullptr, nullptr, m->G, nullptr, m->z,
+             RM_SAFER_U, 0, m->cfg.dim, nullptr};
+  if (m->cfg.model == FRX_CVAR_MF) rc.mode = RM_CVAR_U;
+  int r = run_rows(m, rc);
+  m->ctx->stage_end();
+  return r;
+}
+
+// StepV (safer2.h:493-555): w = z/|hist|, G = U^T diag(z) U over all users, per-item ProjectV.
+static int stage_step_v(frx_model* m, frx_dataset* ds, const float* users) {
+  frx_context* c = m->ctx;
+  c->stage_begin("gramian_Uz");
+  launch_norm_weights(m->z, m->hist_size, m->num_users, m->norm_w, c->stream, &c->launches);
+  int r = gramian_into(m, users, m->num_users, 0, m->cfg.dim, 0, m->cfg.dim, m->z, m->Gz);
+  c->stage_end();
+  if (r) return r;
+  c->stage_begin("step_V");
+  RowCall rc{&ds->by_item, users, m->num_users, m->V, nullptr, nullptr, m->Gz, m->norm_w, nullptr,
+             RM_SAFER_V, 0, m->cfg.dim, nullptr};
+  if (m->cfg.model == FRX_CVAR_MF) rc.mode = RM_CVAR_V;
+  r = run_rows(m, rc);
+  c->stage_end();
+  return r;
+}
+
+// IALSRecommender::Step (ials.h:317-365): Gramian of the fixed side, then per-row Project.
+static int stage_ials_step(frx_model* m, frx_dataset* ds, bool user_side, float* X, const int* xmap,
+                           const Csr* rows_override) {
+  frx_context* c = m->ctx;
+  const float* other = user_side ? m->V : m->U;
+  const int n_other = user_side ? m->num_items : m->num_users;
+  c->stage_begin(user_side ? "gramian_V" : "gramian_U");
+  int r = gramian_into(m, other, n_other, 0, m->cfg.dim, 0, m->cfg.dim, nullptr, m->Gz);
+  c->stage_end();
+  if (r) return r;
+  c->stage_begin(user_side ? "step_U" : "step_V");
+  const Csr* rows = rows_override ? rows_override : (user_side ? &ds->by_user : &ds->by_item);
+  RowCall rc{rows, other, n_other, X, nullptr, xmap, m->Gz, nullptr, nullptr, RM_IALS, 0, m->cfg.dim, nullptr};
+  r = run_rows(m, rc);
+  c->stage_end();
+  return r;
+}
+
+// One block sweep of a ++ model on one side (ialspp.h:351-424, safer2pp.h:448-609).
+static int stage_block(frx_model* m, const Csr* rows, bool user_side, float* X, const int* xmap, int bs,
+                       int be, bool safer, const float* row_w) {
+  frx_context* c = m->ctx;
+  const int d = m->cfg.dim;
+  const float* other = user_side ? m->V : m->U;
+  const int n_other = user_side ? m->num_items : m->num_users;
+  const bool weighted = safer && !user_side;  // safer2pp.h:534-544: (z o U_B)^T U
+  c->stage_begin(user_side ? "block_gramian_V" : "block_gramian_U");
+  if (weighted) launch_norm_weights(m->z, m->hist_size, m->num_users, m->norm_w, c->stream, &c->launches);
+  // strip G[bs:be, 0:d] = E_B^T (w o) E   (contains the B x B block, the reference's TODO ialspp.h:360-361)
+  int r = gramian_into(m, other, n_other, bs, be - bs, 0, d, weighted ? m->z : nullptr, m->Gz);
+  c->stage_end();
+  if (r) return r;
+  c->stage_begin(user_side ? "block_U" : "block_V");
+  RowCall rc{rows, other, n_other, X, nullptr, xmap, m->Gz, weighted ? m->norm_w : nullptr, row_w,
+             safer ? (user_side ? RM_PP_SAFER_U : RM_PP_SAFER_V) : RM_PP_IALS, bs, be - bs, m->pred};
+  r = run_rows(m, rc);
+  c->stage_end();
+  return r;
+}
+
+static int stage_predict(frx_model* m, const Csr* rows, const float* U, const int* xmap) {
+  frx_context* c = m->ctx;
+  c->stage_begin("predict");
+  launch_predict(rows->ptr, rows->col, rows->tup, rows->order, rows->num_order, U, xmap, m->V, m->cfg.dim,
+                 m->pred, c->stream, &c->launches);
+  c->stage_end();
+  CK(cudaGetLastError());
+  return FRX_OK;
+}
+
+#define RC(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
+
+extern "C" int frx_model_initialize(frx_model* m, frx_dataset* ds) {
+  frx_context* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  if (m->is_ials_family()) return FRX_OK;  // run_model.cc:246-257
+  if (ds->by_user.nrows > m->num_users || ds->by_item.nrows > m->num_items)
+    return fail(FRX_ERR_ARG, "dataset ids exceed the model's num_users/num_items");
+  const float* pred = nullptr;
+  if (m->cfg.model == FRX_SAFER2PP) {
+    RC(ensure_pred(m, ds->num_tuples));
+    RC(stage_predict(m, &ds->by_user, m->U, nullptr));
+    pred = m->pred;
+  }
+  RC(stage_user_loss(m, ds, m->G, pred));  // safer2.h:820-821
+  if (m->cfg.model == FRX_SAFER2 || m->cfg.model == FRX_SAFER2PP) RC(stage_xi(m, /*from_mean=*/true));
+  // cvar_mf.h:713 drops its local prev_xi (B-7): xi stays 0.
+  launch_hist_and_item_reg(ds->by_user.ptr, ds->by_user.nrows, m->hist_size, ds->by_item.ptr, ds->by_item.col,
+                           ds->by_item.nrows, m->item_reg, c->stream, &c->launches);
+  CK(cudaGetLastError());
+  return FRX_OK;
+}
+
+extern "C" int frx_model_train(frx_model* m, frx_dataset* ds) {
+  frx_context* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  if (ds->by_user.nrows > m->num_users || ds->by_item.nrows > m->num_items)
+    return fail(FRX_ERR_ARG, "dataset ids exceed the model's num_users/num_items");
+  c->timers_used = 0;
+  const int d = m->cfg.dim, B = m->cfg.block_size;
+  switch (m->cfg.model) {
+    case FRX_IALS:  // ials.h:187-224
+      RC(stage_ials_step(m, ds, true, m->U, nullptr, nullptr));
+      RC(stage_ials_step(m, ds, false, m->V, nullptr, nullptr));
+      RC(stage_item_gramian(m));  // ComputeUserLoss recomputes the Gramian, ials.h:371
+      RC(stage_user_loss(m, ds, m->G, nullptr));
+      break;
+    case FRX_IALSPP:  // ialspp.h:208-261
+      RC(ensure_pred(m, ds->num_tuples));
+      RC(stage_predict(m, &ds->by_user, m->U, nullptr));
+      for (int start = 0; start < d; start += B) {
+        const int end = std::min(start + B, d);
+        RC(stage_block(m, &ds->by_user, true, m->U, nullptr, start, end, false, nullptr));
+        RC(stage_block(m, &ds->by_item, false, m->V, nullptr, start, end, false, nullptr));
+      }
+      break;
+    case FRX_ERM_MF:  // erm_mf.h:257-301
+      RC(stage_step_u(m, ds));
+      RC(stage_step_v(m, ds, m->U));
+      RC(stage_item_gramian(m));
+      RC(stage_user_loss(m, ds, m->G, nullptr));
+      RC(stage_means(m));
+      break;
+    case FRX_CVAR_MF:  // cvar_mf.h:276-330
+      RC(stage_weights(m));
+      CK(cudaMemcpyAsync(m->Uprev, m->U, sizeof(float) * (size_t)m->num_users * d, cudaMemcpyDeviceToDevice,
+                         c->stream));  // cvar_mf.h:282
+      RC(stage_step_u(m, ds));
+      RC(stage_step_v(m, ds, m->Uprev));
+      RC(stage_item_gramian(m));
+      RC(stage_user_loss(m, ds, m->G, nullptr));
+      RC(stage_means(m));
+      RC(stage_xi_exact(m));
+      break;
+    case FRX_SAFER2:  // safer2.h:266-334
+      for (int t = 0; t < m->cfg.pd_iterations; ++t) {
+        RC(stage_weights(m));
+        RC(stage_step_u(m, ds));
+        RC(stage_step_v(m, ds, m->U));
+        RC(stage_item_gramian(m));
+        RC(stage_user_loss(m, ds, m->G, nullptr));
+        RC(stage_means(m));
+      }
+      RC(stage_xi(m, false));
+      break;
+    case FRX_SAFER2PP:  // safer2pp.h:288-355
+      RC(ensure_pred(m, ds->num_tuples));
+      RC(stage_predict(m, &ds->by_user, m->U, nullptr));
+      for (int t = 0; t < m->cfg.pd_iterations; ++t) {
+        RC(stage_weights(m));
+        for (int start = 0; start < d; start += B) {
+          const int end = std::min(start + B, d);
+          RC(stage_block(m, &ds->by_user, true, m->U, nullptr, start, end, true, m->z));
+          RC(stage_block(m, &ds->by_item, false, m->V, nullptr, start, end, true, nullptr));
+        }
+        RC(stage_item_gramian(m));
+        RC(stage_user_loss(m, ds, m->G, m->pred));
+        RC(stage_means(m));
+      }
+      RC(stage_xi(m, false));
+      break;
+  }
+  return FRX_OK;
+}
+
+extern "C" int frx_model_stage(frx_model* m, frx_dataset* ds, int stage) {
+  frx_context* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  const int d = m->cfg.dim;
+  switch (stage) {
+    case 0: return stage_weights(m);
+    case 1: return stage_step_u(m, ds);
+    case 2:
+      if (m->cfg.model == FRX_CVAR_MF) {
+        CK(cudaMemcpyAsync(m->Uprev, m->U, sizeof(float) * (size_t)m->num_users * d, cudaMemcpyDeviceToDevice,
+                           c->stream));
+        return stage_step_v(m, ds, m->Uprev);
+      }
+      return stage_step_v(m, ds, m->U);
+    case 3: return stage_item_gramian(m);
+    case 4:
+      if (m->is_ials_family()) RC(stage_item_gramian(m));
+      return stage_user_loss(m, ds, m->G, nullptr);
+    case 5: return m->cfg.model == FRX_CVAR_MF ? stage_xi_exact(m) : stage_xi(m, false);
+    case 6: return stage_ials_step(m, ds, true, m->U, nullptr, nullptr);
+    case 7: return stage_ials_step(m, ds, false, m->V, nullptr, nullptr);
+  }
+  return fail(FRX_ERR_ARG, "unknown stage %d", stage);
+}
+
+extern "C" int frx_model_get_state(frx_model* m, float* z, float* loss, float* hist_size, float* item_reg,
+                                   float* scalars, float* gramian) {
+  frx_context* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  const size_t d = m->cfg.dim;
+  if (scalars) RC(stage_means(m));
+  if (z) CK(cudaMemcpyAsync(z, m->z, sizeof(float) * m->num_users, cudaMemcpyDeviceToHost, c->stream));
+  if (loss) CK(cudaMemcpyAsync(loss, m->loss, sizeof(float) * m->num_users, cudaMemcpyDeviceToHost, c->stream));
+  if (hist_size) CK(cudaMemcpyAsync(hist_size, m->hist_size, sizeof(float) * m->num_users, cudaMemcpyDeviceToHost, c->stream));
+  if (item_reg) CK(cudaMemcpyAsync(item_reg, m->item_reg, sizeof(float) * m->num_items, cudaMemcpyDeviceToHost, c->stream));
+  if (gramian) CK(cudaMemcpyAsync(gramian, m->G, sizeof(float) * d * d, cudaMemcpyDeviceToHost, c->stream));
+  float sc[4] = {0, 0, 0, 0};
+  if (scalars) CK(cudaMemcpyAsync(sc, m->scal, sizeof(float) * 4, cudaMemcpyDeviceToHost, c->stream));
+  RC(frx_context_sync(c));
+  if (scalars) { scalars[0] = sc[0]; scalars[1] = sc[2]; scalars[2] = sc[1]; }
+  return FRX_OK;
+}
+
+extern "C" int frx_model_set_state(frx_model* m, const float* z, const float* loss, float xi) {
+  frx_context* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  if (z) CK(cudaMemcpyAsync(m->z, z, sizeof(float) * m->num_users, cudaMemcpyHostToDevice, c->stream));
+  if (loss) CK(cudaMemcpyAsync(m->loss, loss, sizeof(float) * m->num_users, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(m->scal, &xi, sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return FRX_OK;
+}
+
+extern "C" int frx_model_last_snr(frx_model* m, int* n_iters, int* n_samples, int* out) {
+  *n_iters = (int)m->last_snr.size();
+  *n_samples = m->last_snr.empty() ? 0 : (int)m->last_snr[0].size();
+  if (out)
+    for (size_t t = 0; t < m->last_snr.size(); ++t)
+      std::copy(m->last_snr[t].begin(), m->last_snr[t].end(), out + t * (size_t)*n_samples);
+  return FRX_OK;
+}
+
+// PrintLosses / ComputeLosses numbers (safer2.h:337-413, ials.h:226-305).
+extern "C" int frx_model_compute_stats(frx_model* m, frx_dataset* ds, double* out6) {
+  frx_context* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  const int d = m->cfg.dim;
+  const int nu = m->num_users, ni = m->num_items;
+  // observed loss: per-user sum of squared residuals in double
+  float* tmp_loss = nullptr;
+  double* obs = nullptr;
+  CK(cudaMalloc(&tmp_loss, sizeof(float) * nu));
+  CK(cudaMalloc(&obs, sizeof(double) * nu));
+  CK(cudaMemsetAsync(obs, 0, sizeof(double) * nu, c->stream));
+  LossParams p;
+  memset(&p, 0, sizeof p);
+  p.ptr = ds->by_user.ptr; p.col = ds->by_user.col; p.tup = ds->by_user.tup;
+  p.order = ds->by_user.order; p.num_rows = ds->by_user.num_order;
+  p.U = m->U; p.V = m->V; p.d = d; p.G = m->G; p.beta = 0.f; p.halve = 0;
+  p.quad = m->quad; p.loss = tmp_loss; p.obs_sq = obs;
+  launch_user_loss(p, nu, c->stream, c->num_sms, &c->launches);
+  std::vector<double> h_obs(nu);
+  std::vector<float> hU((size_t)nu * d), hV((size_t)ni * d), h_ireg(ni), h_loss(nu), GU((size_t)d * d), GV((size_t)d * d);
+  CK(cudaMemcpyAsync(h_obs.data(), obs, sizeof(double) * nu, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(hU.data(), m->U, sizeof(float) * hU.size(), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(hV.data(), m->V, sizeof(float) * hV.size(), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(h_ireg.data(), m->item_reg, sizeof(float) * ni, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(h_loss.data(), m->loss, sizeof(float) * nu, cudaMemcpyDeviceToHost, c->stream));
+  RC(gramian_into(m, m->U, nu, 0, d, 0, d, nullptr, m->Gz));
+  CK(cudaMemcpyAsync(GU.data(), m->Gz, sizeof(float) * GU.size(), cudaMemcpyDeviceToHost, c->stream));
+  float* Gtmp = nullptr;
+  CK(cudaMalloc(&Gtmp, sizeof(float) * (size_t)d * d));
+  RC(gramian_into(m, m->V, ni, 0, d, 0, d, nullptr, Gtmp));
+  CK(cudaMemcpyAsync(GV.data(), Gtmp, sizeof(float) * GV.size(), cudaMemcpyDeviceToHost, c->stream));
+  RC(frx_context_sync(c));
+  cudaFree(tmp_loss); cudaFree(obs); cudaFree(Gtmp);
+  const float uw = m->cfg.uobs_weight;
+  auto ials_reg = [&](int n, int choices) {
+    return (float)((double)m->cfg.reg * std::pow((double)((float)n + uw * (float)choices), (double)m->cfg.reg_exp));
+  };
+  double o = 0, reg = 0, ru = 0, ri = 0;
+  for (int u = 0; u < ds->by_user.nrows; ++u) {
+    const int n = ds->by_user.h_ptr[u + 1] - ds->by_user.h_ptr[u];
+    if (!n) continue;
+    o += h_obs[u];
+    double n2 = 0;
+    for (int k = 0; k < d; ++k) n2 += (double)hU[(size_t)u * d + k] * hU[(size_t)u * d + k];
+    reg += n2 * (m->is_ials_family() ? ials_reg(n, ni) : m->cfg.reg * (1 + uw * ni));
+    ru += n2;
+  }
+  for (int v = 0; v < ds->by_item.nrows; ++v) {
+    const int n = ds->by_item.h_ptr[v + 1] - ds->by_item.h_ptr[v];
+    if (!n) continue;
+    double n2 = 0;
+    for (int k = 0; k < d; ++k) n2 += (double)hV[(size_t)v * d + k] * hV[(size_t)v * d + k];
+    reg += n2 * (m->is_ials_family() ? ials_reg(n, nu) : m->cfg.reg * (h_ireg[v] + m->cfg.alpha * uw * nu));
+    ri += n2;
+  }
+  double unobs = 0;
+  for (size_t k = 0; k < GU.size(); ++k) unobs += (double)GU[k] * GV[k];
+  out6[1] = o / ds->num_tuples;
+  out6[2] = unobs / ni / nu;
+  out6[3] = reg;
+  out6[4] = ru / nu;
+  out6[5] = ri / ni;
+  if (m->is_ials_family()) {
+    out6[0] = o + uw * unobs + reg;
+  } else {
+    double l = 0;
+    for (float x : h_loss) l += x;
+    out6[0] = l;
+  }
+  return FRX_OK;
+}
+
+// EvaluateDataset, safer2.h:225-263 and siblings + recommender.h:78-199.
+extern "C" int frx_model_evaluate(frx_model* m, frx_dataset* tr, frx_dataset* te, const int* k_list, int nk,
+                                  int* user_ids, float* recall, float* ndcg, int* topk, float* folded) {
+  frx_context* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  RC(ensure_eval_maps(tr));
+  const int nu = (int)tr->h_user_ids.size();
+  if (!recall) return nu;
+  if (c->world > 1) return fail(FRX_ERR_ARG, "evaluate: run on a single-rank context");
+  if (tr->by_item.nrows > m->num_items) return fail(FRX_ERR_ARG, "test items exceed the model's num_items");
+  const int d = m->cfg.dim, B = m->cfg.block_size;
+  int max_k = 0;
+  for (int i = 0; i < nk; ++i) max_k = std::max(max_k, k_list[i]);
+  if (nk <= 0 || nk > 32 || max_k <= 0 || max_k > 512) return fail(FRX_ERR_ARG, "bad k_list");
+  float* Ut = nullptr;
+  CK(cudaMalloc(&Ut, sizeof(float) * (size_t)std::max(1, nu) * d));
+  CK(cudaMemsetAsync(Ut, 0, sizeof(float) * (size_t)std::max(1, nu) * d, c->stream));  // MatrixXf::Zero, safer2.h:230
+  switch (m->cfg.model) {
+    case FRX_IALS:  // ials.h:169-174
+      RC(stage_ials_step(m, tr, true, Ut, tr->xmap, nullptr));
+      break;
+    case FRX_ERM_MF:
+    case FRX_CVAR_MF:
+    case FRX_SAFER2: {  // safer2.h:246-252: StepU with weight 1 and the cached item_gramian_
+      RowCall rc{&tr->by_user, m->V, m->num_items, Ut, nullptr, tr->xmap, m->G, nullptr, nullptr,
+                 RM_SAFER_U, 0, d, nullptr};
+      RC(run_rows(m, rc));
+      break;
+    }
+    case FRX_IALSPP:
+    case FRX_SAFER2PP: {  // ialspp.h:152-195, safer2pp.h:223-275: 8 user-only block-sweep epochs
+      float* saved_pred = m->pred;
+      size_t saved_cap = m->pred_cap;
+      m->pred = nullptr; m->pred_cap = 0;
+      RC(ensure_pred(m, tr->num_tuples));
+      CK(cudaMemsetAsync(m->pred, 0, sizeof(float) * (size_t)std::max(1, tr->num_tuples), c->stream));
+      for (int e = 0; e < 8; ++e) {
+        RC(stage_predict(m, &tr->by_user, Ut, tr->xmap));
+        for (int start = 0; start < d; start += B) {
+          const int end = std::min(start + B, d);
+          RC(stage_block(m, &tr->by_user, true, Ut, tr->xmap, start, end, m->cfg.model == FRX_SAFER2PP, nullptr));
+        }
+      }
+      CK(cudaStreamSynchronize(c->stream));
+      cudaFree(m->pred);
+      m->pred = saved_pred; m->pred_cap = saved_cap;
+      break;
+    }
+  }
+  EvalParams p;
+  memset(&p, 0, sizeof p);
+  p.Ut = Ut; p.V = m->V; p.nu = nu; p.num_items = m->num_items; p.d = d;
+  p.user_ids = tr->user_ids_dev;
+  p.tr_ptr = tr->by_user.ptr; p.tr_col = tr->by_user.col;
+  p.te_ptr = te->by_user.ptr; p.te_col = te->by_user.col; p.te_rows = te->by_user.nrows;
+  int* d_k = nullptr; int* d_topk = nullptr; float *d_rec = nullptr, *d_ndcg = nullptr, *d_scores = nullptr;
+  CK(cudaMalloc(&d_k, sizeof(int) * nk));
+  CK(cudaMemcpyAsync(d_k, k_list, sizeof(int) * nk, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMalloc(&d_topk, sizeof(int) * (size_t)std::max(1, nu) * max_k));
+  CK(cudaMalloc(&d_rec, sizeof(float) * (size_t)std::max(1, nu) * nk));
+  CK(cudaMalloc(&d_ndcg, sizeof(float) * (size_t)std::max(1, nu) * nk));
+  size_t chunk = ((size_t)512 << 20) / (sizeof(float) * (size_t)m->num_items);
+  chunk = std::max<size_t>(1, std::min<size_t>(chunk, (size_t)std::max(1, nu)));
+  CK(cudaMalloc(&d_scores, sizeof(float) * chunk * m->num_items));
+  p.k_list = d_k; p.nk = nk; p.max_k = max_k; p.scores = d_scores; p.chunk_users = (int)chunk;
+  p.topk = d_topk; p.recall = d_rec; p.ndcg = d_ndcg;
+  c->stage_begin("evaluate");
+  launch_evaluate(p, c->stream, c->num_sms, &c->launches);
+  c->stage_end();
+  CK(cudaGetLastError());
+  if (nu) {
+    CK(cudaMemcpyAsync(recall, d_rec, sizeof(float) * (size_t)nu * nk, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(ndcg, d_ndcg, sizeof(float) * (size_t)nu * nk, cudaMemcpyDeviceToHost, c->stream));
+    if (topk) CK(cudaMemcpyAsync(topk, d_topk, sizeof(int) * (size_t)nu * max_k, cudaMemcpyDeviceToHost, c->stream));
+    if (folded) CK(cudaMemcpyAsync(folded, Ut, sizeof(float) * (size_t)nu * d, cudaMemcpyDeviceToHost, c->stream));
+    if (user_ids) std::copy(tr->h_user_ids.begin(), tr->h_user_ids.end(), user_ids);
+  }
+  int rc = frx_context_sync(c);
+  cudaFree(Ut); cudaFree(d_k); cudaFree(d_topk); cudaFree(d_rec); cudaFree(d_ndcg); cudaFree(d_scores);
+  if (rc) return rc;
+  return nu;
+}
+
+extern "C" int frx_gramian(frx_context* c, const float* E, int n, int d, const float* w, float* out) {
+  CK(cudaSetDevice(c->device));
+  float *dE = nullptr, *dw = nullptr, *dG = nullptr;
+  CK(cudaMalloc(&dE, sizeof(float) * (size_t)n * d));
+  CK(cudaMalloc(&dG, sizeof(float) * (size_t)d * d));
+  CK(cudaMemcpyAsync(dE, E, sizeof(float) * (size_t)n * d, cudaMemcpyHostToDevice, c->stream));
+  if (w) {
+    CK(cudaMalloc(&dw, sizeof(float) * (size_t)n));
+    CK(cudaMemcpyAsync(dw, w, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  }
+  int rc = c->ensure_gram_ws(gramian_workspace_floats(n, d, d, c->num_sms));
+  if (rc) return rc;
+  launch_gramian(dE, n, d, 0, d, 0, d, dw, dG, d, c->gram_ws, c->gram_ws_floats, c->stream, c->num_sms, &c->launches);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, dG, sizeof(float) * (size_t)d * d, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(dE); cudaFree(dw); cudaFree(dG);
+  return FRX_OK;
+}

@@ -1,0 +1,154 @@
+// Device-side interfaces of the frecsys_b200 CUDA library (sm_100a only).
+// Kernel launchers are plain C++ functions taking a stream; frx_api.cu
+// sequences them into the reference's Train()/EvaluateDataset() stages.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace frx {
+
+// Which reference projection a row-solve launch restates.
+enum RowMode : int {
+  RM_IALS = 0,        // IALSRecommender::Project            ials.h:88-144
+  RM_SAFER_U = 1,     // SAFER2/ERM ProjectU, CVaR ProjectU_eval  safer2.h:104-163
+  RM_SAFER_V = 2,     // SAFER2/ERM ProjectV (stale tail B-1)     safer2.h:166-221
+  RM_CVAR_U = 3,      // CVaRMF ProjectU gradient step (B-3,B-4)  cvar_mf.h:88-134
+  RM_CVAR_V = 4,      // CVaRMF ProjectV gradient step (B-1,B-3)  cvar_mf.h:136-180
+  RM_PP_IALS = 5,     // IALSpp ProjectBlock                  ialspp.h:85-145
+  RM_PP_SAFER_U = 6,  // SAFER2pp ProjectU                    safer2pp.h:97-159
+  RM_PP_SAFER_V = 7   // SAFER2pp ProjectV                    safer2pp.h:161-216
+};
+
+struct RowParams {
+  // sparse rows of the side being solved (CSR by user or CSC by item), file order
+  const int* ptr;
+  const int* col;
+  const int* tup;
+  const int* order;  // non-empty row ids, longest history first
+  int num_rows;      // entries of `order` to process
+  // the fixed side
+  const float* E;  // [num_other x d]
+  int d;
+  int num_other;
+  int cs, bd;  // column block [cs, cs+bd); full-dimension solves use cs=0, bd=d
+  // the side being solved
+  float* X;            // [.. x d]
+  const float* Xread;  // where the current row is read from (CVaR V step reads pre-update copies)
+  const int* xmap;     // row id -> row of X (fold-in evaluation), or null
+  const float* G;      // [d x d] (weighted) Gramian of the fixed side
+  const float* entry_w;   // per fixed-side-row weight w_c = z_c/n_c (item side) or null
+  const float* row_w;     // per-row dual weight z_u (user side) or null (= 1)
+  const float* item_reg;  // item side: sum_{u in hist} 1/n_u
+  float* pred;            // ++ prediction cache, indexed by tuple
+  int mode;
+  float uw, reg, reg_exp, alpha, stepsize;
+  int num_users_total;  // ItemRegularizationValue's num_choices
+  float* scratch;       // per-CTA global matrices when the system does not fit in shared memory
+  size_t scratch_stride;
+  int use_smem_matrix;
+  int* status;  // set non-zero on a non-positive pivot
+};
+
+void launch_row_solve_generic(const RowParams& p, cudaStream_t s, int num_sms, long long* launches);
+size_t row_solve_generic_scratch_floats(int bd);  // per-CTA scratch (0 if shared memory suffices)
+int row_solve_generic_grid(int num_rows, int num_sms);
+
+// out[bd x fd] = sum_r w[r] * E[r][cs+i] * E[r][fs+j]; two-stage, deterministic.
+void launch_gramian(const float* E, int n, int d, int cs, int bd, int fs, int fd, const float* w,
+                    float* out, int ld_out, float* workspace, size_t workspace_floats,
+                    cudaStream_t s, int num_sms, long long* launches);
+size_t gramian_workspace_floats(int n, int bd, int fd, int num_sms);
+
+struct LossParams {
+  const int* ptr;
+  const int* col;
+  const int* tup;
+  const int* order;
+  int num_rows;
+  const float* U;
+  const float* V;
+  int d;
+  const float* G;       // item Gramian
+  const float* pred;    // SAFER2++: cached predictions (else null)
+  float beta;           // unobserved weight
+  int halve;            // SAFER2-family /2 (safer2.h:99); iALS family not (ials.h:70-86)
+  float* quad;          // [num_users] scratch: u^T G u
+  float* loss;          // [num_users] out (rows without history untouched)
+  double* obs_sq;       // optional [num_users]: sum (pred-1)^2 in double (stats)
+};
+void launch_user_loss(const LossParams& p, int num_users, cudaStream_t s, int num_sms,
+                      long long* launches);
+
+// pred[t] = v_i . u for every tuple (PredictDataset ialspp.h:469-517).
+void launch_predict(const int* ptr, const int* col, const int* tup, const int* order, int num_rows,
+                    const float* U, const int* xmap, const float* V, int d, float* pred,
+                    cudaStream_t s, long long* launches);
+
+// z_u update (safer2.h:745-794, safer2pp.h:839-862, cvar_mf.h:597-642).
+// kind: 0 gaussian, 1 epanechnikov, 2 indicator.  only_with_history: skip rows with hist_size==0.
+void launch_user_weights(const float* loss, const float* hist_size, int num_users, float* z,
+                         const float* xi_dev, float bandwidth, int kind, int only_with_history,
+                         cudaStream_t s, long long* launches);
+
+// Newton / Armijo xi estimation (safer2.h:652-742) in one cooperative kernel.
+// xi_io: device scalar, in = start value, out = result.  If start_from_mean,
+// the start value is mean(loss) (Initialize, safer2.h:822).
+struct XiParams {
+  const float* loss;
+  int num_users;
+  const int* snr_idx;  // [iters x n_samples] or null
+  int n_samples;
+  int iters;
+  float alpha, bandwidth;
+  int epanechnikov;
+  int start_from_mean;
+  float* xi_io;
+  double* partials;  // [2][grid][3]
+  unsigned* barrier; // [2] zero-initialised
+};
+int launch_xi_newton(const XiParams& p, cudaStream_t s, int num_sms, long long* launches);
+size_t xi_partials_doubles(int num_sms);
+
+// Exact quantile (cvar_mf.h:582-595): -vals[Q] where vals = sorted(-loss), Q = (size_t)(n*alpha).
+void launch_exact_quantile(const float* loss, int n, float alpha, float* xi_out, unsigned* hist_ws,
+                           cudaStream_t s, long long* launches);
+
+// mean(z), mean(z*loss) in double -> scalars_out[0..1] (float)
+void launch_weight_means(const float* z, const float* loss, int n, float* out2, double* ws,
+                         cudaStream_t s, long long* launches);
+
+// Initialize(): hist_size[u] = n_u; item_reg[v] = sum_{u in hist(v)} 1/n_u (safer2.h:826-837)
+void launch_hist_and_item_reg(const int* uptr, int num_users_ds, float* hist_size, const int* iptr,
+                              const int* icol, int num_items_ds, float* item_reg, cudaStream_t s,
+                              long long* launches);
+
+// norm_w[u] = z[u] / hist_size[u] (safer2.h:502-503)
+void launch_norm_weights(const float* z, const float* hist_size, int n, float* out, cudaStream_t s,
+                         long long* launches);
+
+void launch_fill(float* p, size_t n, float v, cudaStream_t s, long long* launches);
+
+// Evaluation (recommender.h:78-199): scores = Ut * V^T tile by tile, history
+// mask, per-user top-k, Recall/NDCG.
+struct EvalParams {
+  const float* Ut;  // [nu x d] folded-in users
+  const float* V;   // [num_items x d]
+  int nu, num_items, d;
+  const int* user_ids;               // [nu] ascending ids
+  const int* tr_ptr; const int* tr_col;  // test_tr CSR (history to mask)
+  const int* te_ptr; const int* te_col;  // test_te CSR (ground truth)
+  int te_rows;                       // rows available in te_ptr
+  const int* k_list; int nk; int max_k;
+  float* scores;                     // [chunk_users x num_items] workspace
+  int chunk_users;
+  int* topk;                         // [nu x max_k]
+  float* recall; float* ndcg;        // [nu x nk]
+};
+void launch_evaluate(const EvalParams& p, cudaStream_t s, int num_sms, long long* launches);
+
+// Dataset build: stable sort of tuple ids by row id -> ptr/col/tup (dataset.h:86-91).
+void build_csr(const int* d_keys, const int* d_other, int n, int nrows, int* ptr, int* col, int* tup,
+               cudaStream_t s, long long* launches);
+
+}  // namespace frx

@@ -1,0 +1,631 @@
+// Side stages of the epoch: Gramians, per-user loss, dual weights, the
+// smoothed-quantile Newton iteration, exact quantile, prediction cache and the
+// one-off Initialize() reductions.  Reference citations are per kernel.
+#include "frx_kernels.cuh"
+#include <cooperative_groups.h>
+#include <cfloat>
+
+namespace cg = cooperative_groups;
+
+namespace frx {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of a double; result valid in every thread.  blockDim <= 1024.
+__device__ double block_sum_d(double v, double* sh /*[33]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum_d(v);
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    double t = lane < nw ? sh[lane] : 0.0;
+    t = warp_sum_d(t);
+    if (lane == 0) sh[32] = t;
+  }
+  __syncthreads();
+  return sh[32];
+}
+
+// ---------------------------------------------------------------------------
+// Gramian, SIMT two-stage version: partial tiles per row slab, then a fixed-order
+// reduction (deterministic).  Restates `X.transpose() * Y` at ials.h:321,
+// safer2.h:55,294-295,504-509 and the block forms ialspp.h:356-365,
+// safer2pp.h:534-544.
+// ---------------------------------------------------------------------------
+constexpr int GT = 64;   // output tile edge
+constexpr int GK = 32;   // rows per staged chunk
+
+__global__ void __launch_bounds__(256) gramian_partial_kernel(
+    const float* __restrict__ E, int n, int d, int cs, int bd, int fs, int fd,
+    const float* __restrict__ w, float* __restrict__ ws, int rows_per_slab, int tiles_j) {
+  __shared__ __align__(16) float As[GK][GT];
+  __shared__ __align__(16) float Bs[GK][GT];
+  const int tile = blockIdx.y;
+  const int i0 = (tile / tiles_j) * GT, j0 = (tile % tiles_j) * GT;
+  const int slab = blockIdx.x;
+  const int r_begin = slab * rows_per_slab;
+  const int r_end = min(n, r_begin + rows_per_slab);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  for (int r0 = r_begin; r0 < r_end; r0 += GK) {
+    for (int idx = threadIdx.x; idx < GK * GT; idx += 256) {
+      const int rr = idx / GT, c = idx % GT;
+      const int row = r0 + rr;
+      float a = 0.f, b = 0.f;
+      if (row < r_end) {
+        const float* er = E + (size_t)row * d;
+        const float wr = w ? w[row] : 1.f;
+        if (i0 + c < bd) a = er[cs + i0 + c] * wr;
+        if (j0 + c < fd) b = er[fs + j0 + c];
+      }
+      As[rr][c] = a;
+      Bs[rr][c] = b;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int rr = 0; rr < GK; ++rr) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[rr][4 * ty]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[rr][4 * tx]);
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+    }
+    __syncthreads();
+  }
+  float* out = ws + ((size_t)slab * gridDim.y + tile) * (GT * GT);
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) out[(4 * ty + a) * GT + 4 * tx + b] = acc[a][b];
+}
+
+__global__ void gramian_reduce_kernel(const float* __restrict__ ws, int slabs, int tiles, int tiles_j,
+                                      int bd, int fd, float* __restrict__ out, int ld_out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= bd * fd) return;
+  const int i = idx / fd, j = idx % fd;
+  const int tile = (i / GT) * tiles_j + (j / GT);
+  const int off = (i % GT) * GT + (j % GT);
+  float s = 0.f;
+  for (int sl = 0; sl < slabs; ++sl) s += ws[((size_t)sl * tiles + tile) * (GT * GT) + off];
+  out[(size_t)i * ld_out + j] = s;
+}
+
+int gramian_slabs(int n, int tiles, int num_sms) {
+  int want = (4 * num_sms + tiles - 1) / tiles;  // ~4 waves of CTAs
+  int max_slabs = (n + 255) / 256;               // at least 256 rows per slab
+  if (max_slabs < 1) max_slabs = 1;
+  if (want > max_slabs) want = max_slabs;
+  if (want < 1) want = 1;
+  return want;
+}
+
+// ---------------------------------------------------------------------------
+// Kernel functions of the smoothed quantile, safer2.h:599-647.  float in/out,
+// double bodies, exactly the promotions of the reference expressions
+// (SURVEY.md D.4); B-14: float fabs.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float gaussian_kernel(const float u, const float h) {
+  return (float)(pow(2 * 3.14159265358979323846, -0.5) *
+                 exp(-pow((double)(u / h) * 0.70710678118654752440, 2.0)) / (double)h);
+}
+__device__ __forceinline__ float gaussian_kernel_cdf(const float u, const float h) {
+  return (float)(0.5 * erfc((double)(-(u / h)) * 0.70710678118654752440));
+}
+__device__ __forceinline__ float gaussian_loss(const float u, const float h, const float alpha) {
+  const float ell = h * gaussian_kernel(u, h) + (u / h) * (1 - 2 * gaussian_kernel_cdf(-u, h));
+  return (float)((double)((h / 2) * ell) + ((double)(1 - alpha) - 0.5) * (double)u);
+}
+__device__ __forceinline__ float epanechnikov_kernel(const float u, const float h) {
+  const float uh = u / h;
+  return (float)((3.0 / 4.0) * (1 - pow((double)uh, 2.0)) * (int)(fabsf(uh) < 1) / (double)h);
+}
+__device__ __forceinline__ float epanechnikov_kernel_cdf(const float u, const float h) {
+  const float uh = u / h;
+  const int in_supp = (int)(fabsf(uh) <= 1);
+  const int pos = (int)(uh > 1);
+  const double hd = h, ud = u;
+  return (float)(((pow(hd, -3.0) / 4.0) *
+                  (((double)(3 * u) * pow(hd, 2.0) - pow(ud, 3.0)) + 2 * pow(hd, 3.0)) * in_supp) +
+                 (1 - in_supp) * pos);
+}
+__device__ __forceinline__ float epanechnikov_loss(const float u, const float h, const float alpha) {
+  const float uh = u / h;
+  const int in_supp = (int)(fabsf(uh) <= 1);
+  const int pos = (int)(uh > 1);
+  const float ell = (float)(((3.0 / 4.0) * pow((double)uh, 2.0) - (1.0 / 8.0) * pow((double)uh, 4.0) +
+                             (3.0 / 8.0)) * in_supp + (double)(fabsf(uh) * pos));
+  return (float)((1.0 / 2.0) * (double)h * (double)ell + ((double)(1 - alpha) - 0.5) * (double)u);
+}
+
+// ---------------------------------------------------------------------------
+// u^T G u for a tile of users (the `ireg` of ComputeLoss, safer2.h:97).
+// ---------------------------------------------------------------------------
+constexpr int QU = 16;  // users per CTA
+__global__ void __launch_bounds__(256) quadform_kernel(const float* __restrict__ U, int num_users, int d,
+                                                       const float* __restrict__ G, float* __restrict__ quad) {
+  extern __shared__ __align__(16) float sh[];
+  float* Us = sh;                 // [QU][dp]
+  const int dp = (d + 3) & ~3;
+  float* red = sh + QU * dp;      // [QU][8 warps]
+  const int u0 = blockIdx.x * QU;
+  for (int idx = threadIdx.x; idx < QU * dp; idx += 256) {
+    const int uu = idx / dp, k = idx % dp;
+    Us[idx] = (u0 + uu < num_users && k < d) ? U[(size_t)(u0 + uu) * d + k] : 0.f;
+  }
+  __syncthreads();
+  float tot[QU];
+#pragma unroll
+  for (int uu = 0; uu < QU; ++uu) tot[uu] = 0.f;
+  for (int j = threadIdx.x; j < d; j += 256) {
+    float acc[QU];
+#pragma unroll
+    for (int uu = 0; uu < QU; ++uu) acc[uu] = 0.f;
+    int i = 0;
+    for (; i + 4 <= d; i += 4) {
+      const float g0 = __ldg(G + (size_t)(i + 0) * d + j), g1 = __ldg(G + (size_t)(i + 1) * d + j);
+      const float g2 = __ldg(G + (size_t)(i + 2) * d + j), g3 = __ldg(G + (size_t)(i + 3) * d + j);
+#pragma unroll
+      for (int uu = 0; uu < QU; ++uu) {
+        const float4 u4 = *reinterpret_cast<const float4*>(&Us[uu * dp + i]);
+        acc[uu] = fmaf(u4.x, g0, acc[uu]);
+        acc[uu] = fmaf(u4.y, g1, acc[uu]);
+        acc[uu] = fmaf(u4.z, g2, acc[uu]);
+        acc[uu] = fmaf(u4.w, g3, acc[uu]);
+      }
+    }
+    for (; i < d; ++i) {
+      const float g0 = __ldg(G + (size_t)i * d + j);
+#pragma unroll
+      for (int uu = 0; uu < QU; ++uu) acc[uu] = fmaf(Us[uu * dp + i], g0, acc[uu]);
+    }
+#pragma unroll
+    for (int uu = 0; uu < QU; ++uu) tot[uu] = fmaf(acc[uu], Us[uu * dp + j], tot[uu]);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int uu = 0; uu < QU; ++uu) {
+    const float v = warp_sum(tot[uu]);
+    if (lane == 0) red[uu * 8 + warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < QU && u0 + threadIdx.x < num_users) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[threadIdx.x * 8 + w];
+    quad[u0 + threadIdx.x] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Per-user loss, ComputeLoss safer2.h:85-101 / ials.h:70-86 / safer2pp.h:80-95.
+// One warp per user; the squared residuals are added in history (file) order
+// into a float through a double, as `loss += pow(x - 1, 2.0)` does.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) user_loss_kernel(LossParams p) {
+  extern __shared__ __align__(16) float sh[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int d = p.d;
+  float* us = sh + warp * ((d + 3) & ~3);
+  const int gw = blockIdx.x * 8 + warp;
+  const int stride = gridDim.x * 8;
+  for (int ri = gw; ri < p.num_rows; ri += stride) {
+    const int u = p.order[ri];
+    const int beg = p.ptr[u], n = p.ptr[u + 1] - beg;
+    float loss = 0.f;
+    double obs = 0.0;
+    if (p.pred) {
+      // safer2pp.h:86-89: residuals from the cached predictions
+      double part = 0.0;
+      for (int e = lane; e < n; e += 32) {
+        const float x = p.pred[p.tup[beg + e]] - 1.f;
+        part += (double)x * (double)x;
+      }
+      obs = warp_sum_d(part);
+      loss = (float)obs;
+    } else {
+      __syncwarp();
+      for (int k = lane; k < d; k += 32) us[k] = p.U[(size_t)u * d + k];
+      __syncwarp();
+      int e = 0;
+      for (; e + 4 <= n; e += 4) {
+        const float* v0 = p.V + (size_t)p.col[beg + e] * d;
+        const float* v1 = p.V + (size_t)p.col[beg + e + 1] * d;
+        const float* v2 = p.V + (size_t)p.col[beg + e + 2] * d;
+        const float* v3 = p.V + (size_t)p.col[beg + e + 3] * d;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int k = lane; k < d; k += 32) {
+          const float uk = us[k];
+          a0 = fmaf(__ldg(v0 + k), uk, a0);
+          a1 = fmaf(__ldg(v1 + k), uk, a1);
+          a2 = fmaf(__ldg(v2 + k), uk, a2);
+          a3 = fmaf(__ldg(v3 + k), uk, a3);
+        }
+        a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+        const double s0 = (double)(a0 - 1.f), s1 = (double)(a1 - 1.f);
+        const double s2 = (double)(a2 - 1.f), s3 = (double)(a3 - 1.f);
+        loss = (float)((double)loss + s0 * s0);
+        loss = (float)((double)loss + s1 * s1);
+        loss = (float)((double)loss + s2 * s2);
+        loss = (float)((double)loss + s3 * s3);
+        obs += s0 * s0 + s1 * s1 + s2 * s2 + s3 * s3;
+      }
+      for (; e < n; ++e) {
+        const float* v0 = p.V + (size_t)p.col[beg + e] * d;
+        float a0 = 0.f;
+        for (int k = lane; k < d; k += 32) a0 = fmaf(__ldg(v0 + k), us[k], a0);
+        a0 = warp_sum(a0);
+        const double s0 = (double)(a0 - 1.f);
+        loss = (float)((double)loss + s0 * s0);
+        obs += s0 * s0;
+      }
+    }
+    if (lane == 0) {
+      loss /= (float)n;
+      loss += p.beta * p.quad[u];
+      if (p.halve) loss *= 0.5f;
+      p.loss[u] = loss;
+      if (p.obs_sq) p.obs_sq[u] = obs;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) predict_kernel(const int* __restrict__ ptr, const int* __restrict__ col,
+                                                      const int* __restrict__ tup, const int* __restrict__ order,
+                                                      int num_rows, const float* __restrict__ U,
+                                                      const int* __restrict__ xmap, const float* __restrict__ V,
+                                                      int d, float* __restrict__ pred) {
+  extern __shared__ __align__(16) float sh[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* us = sh + warp * ((d + 3) & ~3);
+  for (int ri = blockIdx.x * 8 + warp; ri < num_rows; ri += gridDim.x * 8) {
+    const int u = order[ri];
+    const int xr = xmap ? xmap[u] : u;
+    const int beg = ptr[u], n = ptr[u + 1] - beg;
+    __syncwarp();
+    for (int k = lane; k < d; k += 32) us[k] = U[(size_t)xr * d + k];
+    __syncwarp();
+    for (int e = 0; e < n; ++e) {
+      const float* v = V + (size_t)col[beg + e] * d;
+      float a = 0.f;
+      for (int k = lane; k < d; k += 32) a = fmaf(__ldg(v + k), us[k], a);
+      a = warp_sum(a);
+      if (lane == 0) pred[tup[beg + e]] = a;
+    }
+  }
+}
+
+__global__ void user_weights_kernel(const float* __restrict__ loss, const float* __restrict__ hist_size,
+                                    int n, float* __restrict__ z, const float* __restrict__ xi_dev,
+                                    float h, int kind, int only_with_history) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n) return;
+  if (only_with_history && !(hist_size[u] > 0.f)) return;
+  const float xi = *xi_dev;
+  const float r = loss[u] - xi;
+  float nw;
+  if (kind == 2) nw = (r >= 0) ? 1.f : 0.f;                          // cvar_mf.h:623
+  else if (kind == 1) nw = 1 - epanechnikov_kernel_cdf(-r, h);       // safer2.h:773
+  else nw = 1 - gaussian_kernel_cdf(-r, h);                          // safer2.h:775
+  z[u] = nw;
+}
+
+// ---------------------------------------------------------------------------
+// xi: Newton-Raphson with Armijo backtracking on the smoothed quantile
+// objective, safer2.h:652-742, all iterations in ONE cooperative kernel.  Every
+// EvaluateQuantile is a grid-wide 3-way reduction: per-CTA partial sums in
+// double -> grid barrier -> every CTA adds the partials in the same fixed order,
+// so all CTAs take identical branches.
+// ---------------------------------------------------------------------------
+struct QEval { float value, grad, H; };
+
+__device__ QEval evaluate_quantile(const XiParams& p, const int* idx, int n, float xi, int parity,
+                                   double* sh, cg::grid_group& grid) {
+  double s_cdf = 0.0, s_pdf = 0.0, s_loss = 0.0;
+  const float h = p.bandwidth, alpha = p.alpha;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float l = idx ? p.loss[idx[i]] : p.loss[i];
+    const float u = l - xi;
+    if (p.epanechnikov) {
+      s_cdf += epanechnikov_kernel_cdf(-u, h);
+      s_pdf += epanechnikov_kernel(-u, h);
+      s_loss += epanechnikov_loss(u, h, alpha);
+    } else {
+      s_cdf += gaussian_kernel_cdf(-u, h);
+      s_pdf += gaussian_kernel(-u, h);
+      s_loss += gaussian_loss(u, h, alpha);
+    }
+  }
+  s_cdf = block_sum_d(s_cdf, sh);
+  s_pdf = block_sum_d(s_pdf, sh);
+  s_loss = block_sum_d(s_loss, sh);
+  double* part = p.partials + (size_t)parity * gridDim.x * 3;
+  if (threadIdx.x == 0) {
+    part[blockIdx.x * 3 + 0] = s_cdf;
+    part[blockIdx.x * 3 + 1] = s_pdf;
+    part[blockIdx.x * 3 + 2] = s_loss;
+  }
+  grid.sync();
+  double t_cdf = 0.0, t_pdf = 0.0, t_loss = 0.0;
+  for (int b = 0; b < (int)gridDim.x; ++b) {
+    t_cdf += part[b * 3 + 0];
+    t_pdf += part[b * 3 + 1];
+    t_loss += part[b * 3 + 2];
+  }
+  const float mean_cdf = (float)(t_cdf / n), mean_pdf = (float)(t_pdf / n), mean_loss = (float)(t_loss / n);
+  QEval q;
+  q.grad = (-(1 - alpha) + mean_cdf) / alpha;  // safer2.h:659-686
+  q.H = mean_pdf / alpha;
+  q.value = mean_loss / alpha;
+  return q;
+}
+
+__global__ void __launch_bounds__(256) xi_newton_kernel(XiParams p) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sh[33];
+  int parity = 0;
+  float xi;
+  if (p.start_from_mean) {  // Initialize: prev_xi = user_loss_.mean() (safer2.h:822)
+    double s = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.num_users; i += gridDim.x * blockDim.x)
+      s += (double)p.loss[i];
+    s = block_sum_d(s, sh);
+    double* part = p.partials + (size_t)parity * gridDim.x * 3;
+    if (threadIdx.x == 0) part[blockIdx.x * 3] = s;
+    grid.sync();
+    double t = 0.0;
+    for (int b = 0; b < (int)gridDim.x; ++b) t += part[b * 3];
+    xi = (float)(t / p.num_users);
+    parity ^= 1;
+  } else {
+    xi = *p.xi_io;
+  }
+  for (int t = 0; t < p.iters; ++t) {
+    const int* idx = p.snr_idx ? p.snr_idx + (size_t)t * p.n_samples : nullptr;
+    const int n = p.snr_idx ? p.n_samples : p.num_users;
+    // ComputeXiDirection, safer2.h:692-712
+    const QEval e0 = evaluate_quantile(p, idx, n, xi, parity, sh, grid);
+    parity ^= 1;
+    const float d = e0.grad / e0.H;
+    const float c = 1e-4f;
+    float gamma = 1.0f;
+    float x = xi + gamma * (-d);
+    for (int k = 0; k < 32; k++) {
+      const QEval ex = evaluate_quantile(p, idx, n, x, parity, sh, grid);
+      parity ^= 1;
+      if (ex.value > e0.value + c * gamma * ex.grad * (-d)) {  // B-6: trial point's gradient
+        gamma *= 0.5f;
+        x = xi + gamma * (-d);
+      } else {
+        break;
+      }
+    }
+    xi = xi + (-gamma * d);
+  }
+  grid.sync();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *p.xi_io = xi;
+}
+
+// ---------------------------------------------------------------------------
+// Exact quantile, cvar_mf.h:582-595: nth_element of -loss at Q=(size_t)(n*alpha),
+// returned negated.  Single-CTA 4-pass radix select on order-preserving keys.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned f2key(float f) {
+  const unsigned b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(unsigned k) {
+  const unsigned b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(b);
+}
+
+__global__ void __launch_bounds__(1024) exact_quantile_kernel(const float* __restrict__ loss, int n, float alpha,
+                                                              float* __restrict__ xi_out) {
+  __shared__ unsigned hist[256];
+  __shared__ unsigned s_prefix, s_rank;
+  const float Qf = (float)n * alpha;  // vals.size() * alpha_  (float product)
+  unsigned rank = (unsigned)(size_t)Qf;  // 0-based rank in ascending order of -loss
+  if (rank >= (unsigned)n) rank = n - 1;
+  unsigned prefix = 0, mask = 0;
+  for (int pass = 3; pass >= 0; --pass) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned k = f2key(-loss[i]);
+      if ((k & mask) == prefix) atomicAdd(&hist[(k >> (8 * pass)) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned acc = 0;
+      int b = 0;
+      for (; b < 256; ++b) {
+        if (acc + hist[b] > rank) break;
+        acc += hist[b];
+      }
+      if (b > 255) b = 255;
+      s_prefix = prefix | ((unsigned)b << (8 * pass));
+      s_rank = rank - acc;
+    }
+    __syncthreads();
+    prefix = s_prefix;
+    rank = s_rank;
+    mask |= 0xffu << (8 * pass);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *xi_out = -key2f(prefix);
+}
+
+__global__ void __launch_bounds__(256) weight_means_partial(const float* __restrict__ z, const float* __restrict__ loss,
+                                                            int n, double* __restrict__ ws) {
+  __shared__ double sh[33];
+  double a = 0.0, b = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    a += (double)z[i];
+    b += (double)(z[i] * loss[i]);  // (dual_weight_.array() * user_loss_.array()).mean(), safer2.h:300
+  }
+  a = block_sum_d(a, sh);
+  b = block_sum_d(b, sh);
+  if (threadIdx.x == 0) { ws[blockIdx.x * 2] = a; ws[blockIdx.x * 2 + 1] = b; }
+}
+__global__ void weight_means_final(const double* __restrict__ ws, int nb, int n, float* __restrict__ out2) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < nb; ++i) { a += ws[i * 2]; b += ws[i * 2 + 1]; }
+    out2[0] = (float)(a / n);
+    out2[1] = (float)(b / n);
+  }
+}
+
+__global__ void hist_size_kernel(const int* __restrict__ uptr, int rows, float* __restrict__ hist_size) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u < rows) {
+    const int n = uptr[u + 1] - uptr[u];
+    if (n > 0) hist_size[u] = (float)n;  // safer2.h:826-829
+  }
+}
+// item_reg_(v) += 1.0 / user_history_size_(u) in item-history order, float += double (safer2.h:830-837)
+__global__ void item_reg_kernel(const int* __restrict__ iptr, const int* __restrict__ icol, int rows,
+                                const float* __restrict__ hist_size, float* __restrict__ item_reg) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= rows) return;
+  float acc = item_reg[v];
+  for (int t = iptr[v]; t < iptr[v + 1]; ++t) acc = (float)((double)acc + 1.0 / (double)hist_size[icol[t]]);
+  item_reg[v] = acc;
+}
+__global__ void norm_weights_kernel(const float* __restrict__ z, const float* __restrict__ hs, int n,
+                                    float* __restrict__ out) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u < n) out[u] = z[u] / hs[u];
+}
+__global__ void fill_kernel(float* p, size_t n, float v) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace
+
+size_t gramian_workspace_floats(int n, int bd, int fd, int num_sms) {
+  const int tiles = ((bd + GT - 1) / GT) * ((fd + GT - 1) / GT);
+  return (size_t)gramian_slabs(n, tiles, num_sms) * tiles * GT * GT;
+}
+
+void launch_gramian(const float* E, int n, int d, int cs, int bd, int fs, int fd, const float* w,
+                    float* out, int ld_out, float* workspace, size_t workspace_floats,
+                    cudaStream_t s, int num_sms, long long* launches) {
+  const int tiles_i = (bd + GT - 1) / GT, tiles_j = (fd + GT - 1) / GT;
+  const int tiles = tiles_i * tiles_j;
+  const int slabs = gramian_slabs(n, tiles, num_sms);
+  (void)workspace_floats;
+  int rows_per_slab = (n + slabs - 1) / slabs;
+  rows_per_slab = ((rows_per_slab + GK - 1) / GK) * GK;
+  dim3 grid(slabs, tiles);
+  gramian_partial_kernel<<<grid, 256, 0, s>>>(E, n, d, cs, bd, fs, fd, w, workspace, rows_per_slab, tiles_j);
+  gramian_reduce_kernel<<<(bd * fd + 255) / 256, 256, 0, s>>>(workspace, slabs, tiles, tiles_j, bd, fd, out, ld_out);
+  if (launches) *launches += 2;
+}
+
+void launch_user_loss(const LossParams& p, int num_users, cudaStream_t s, int num_sms, long long* launches) {
+  const int d = p.d, dp = (d + 3) & ~3;
+  {
+    const size_t smem = sizeof(float) * (size_t)(QU * dp + QU * 8);
+    cudaFuncSetAttribute(quadform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    quadform_kernel<<<(num_users + QU - 1) / QU, 256, smem, s>>>(p.U, num_users, d, p.G, p.quad);
+    if (launches) ++*launches;
+  }
+  if (p.num_rows > 0) {
+    const size_t smem = sizeof(float) * (size_t)(8 * dp);
+    int grid = (p.num_rows + 7) / 8;
+    const int cap = num_sms * 8;
+    if (grid > cap) grid = cap;
+    cudaFuncSetAttribute(user_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    user_loss_kernel<<<grid, 256, smem, s>>>(p);
+    if (launches) ++*launches;
+  }
+}
+
+void launch_predict(const int* ptr, const int* col, const int* tup, const int* order, int num_rows,
+                    const float* U, const int* xmap, const float* V, int d, float* pred,
+                    cudaStream_t s, long long* launches) {
+  if (num_rows <= 0) return;
+  const size_t smem = sizeof(float) * (size_t)(8 * ((d + 3) & ~3));
+  int grid = (num_rows + 7) / 8;
+  if (grid > 148 * 8) grid = 148 * 8;
+  cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  predict_kernel<<<grid, 256, smem, s>>>(ptr, col, tup, order, num_rows, U, xmap, V, d, pred);
+  if (launches) ++*launches;
+}
+
+void launch_user_weights(const float* loss, const float* hist_size, int num_users, float* z,
+                         const float* xi_dev, float bandwidth, int kind, int only_with_history,
+                         cudaStream_t s, long long* launches) {
+  user_weights_kernel<<<(num_users + 255) / 256, 256, 0, s>>>(loss, hist_size, num_users, z, xi_dev,
+                                                             bandwidth, kind, only_with_history);
+  if (launches) ++*launches;
+}
+
+size_t xi_partials_doubles(int num_sms) { return (size_t)2 * num_sms * 3; }
+
+int launch_xi_newton(const XiParams& p_in, cudaStream_t s, int num_sms, long long* launches) {
+  XiParams p = p_in;
+  const int n = p.snr_idx ? p.n_samples : p.num_users;
+  int work = n > p.num_users ? n : (p.start_from_mean ? p.num_users : n);
+  int grid = (work + 255) / 256;
+  if (grid > num_sms) grid = num_sms;
+  if (grid < 1) grid = 1;
+  void* args[] = {&p};
+  cudaError_t e = cudaLaunchCooperativeKernel((void*)xi_newton_kernel, dim3(grid), dim3(256), args, 0, s);
+  if (launches) ++*launches;
+  return e == cudaSuccess ? 0 : -1;
+}
+
+void launch_exact_quantile(const float* loss, int n, float alpha, float* xi_out, unsigned* hist_ws,
+                           cudaStream_t s, long long* launches) {
+  (void)hist_ws;
+  exact_quantile_kernel<<<1, 1024, 0, s>>>(loss, n, alpha, xi_out);
+  if (launches) ++*launches;
+}
+
+void launch_weight_means(const float* z, const float* loss, int n, float* out2, double* ws,
+                         cudaStream_t s, long long* launches) {
+  int nb = (n + 255) / 256;
+  if (nb > 128) nb = 128;
+  weight_means_partial<<<nb, 256, 0, s>>>(z, loss, n, ws);
+  weight_means_final<<<1, 32, 0, s>>>(ws, nb, n, out2);
+  if (launches) *launches += 2;
+}
+
+void launch_hist_and_item_reg(const int* uptr, int num_users_ds, float* hist_size, const int* iptr,
+                              const int* icol, int num_items_ds, float* item_reg, cudaStream_t s,
+                              long long* launches) {
+  if (num_users_ds > 0) hist_size_kernel<<<(num_users_ds + 255) / 256, 256, 0, s>>>(uptr, num_users_ds, hist_size);
+  if (num_items_ds > 0) item_reg_kernel<<<(num_items_ds + 127) / 128, 128, 0, s>>>(iptr, icol, num_items_ds, hist_size, item_reg);
+  if (launches) *launches += 2;
+}
+
+void launch_norm_weights(const float* z, const float* hist_size, int n, float* out, cudaStream_t s,
+                         long long* launches) {
+  norm_weights_kernel<<<(n + 255) / 256, 256, 0, s>>>(z, hist_size, n, out);
+  if (launches) ++*launches;
+}
+
+void launch_fill(float* p, size_t n, float v, cudaStream_t s, long long* launches) {
+  if (n == 0) return;
+  fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, n, v);
+  if (launches) ++*launches;
+}
+
+}  // namespace frx

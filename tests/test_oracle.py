@@ -1,0 +1,103 @@
+"""CPU tests of the oracle itself: it must reproduce the reference's own test
+conditions on the reference's bundled ML-1M fixture (the only result-pinning facts
+the reference holds — there are no golden vectors) and the committed
+golden summary produced by tests/golden/make_golden.py."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from oracle import loader as O
+
+
+@pytest.fixture(scope="module")
+def data():
+    return (O.Dataset.from_csv(helpers.fixture_csv("train")),
+            O.Dataset.from_csv(helpers.fixture_csv("validation_tr")),
+            O.Dataset.from_csv(helpers.fixture_csv("validation_te")))
+
+
+def test_dataset_matches_reference_fixture_facts(data):
+    tr, vtr, vte = data
+    # 388,246 tuples / 4,034 users / 3,468 items; 1,000 held-out users 4034-5033
+    assert (tr.num_tuples, tr.distinct_users, tr.distinct_items) == (388246, 4034, 3468)
+    assert (tr.max_user, tr.max_item) == (4033, 3467)
+    assert (vtr.num_tuples, vte.num_tuples) == (74132, 18026)
+    assert vtr.distinct_users == vte.distinct_users == 1000
+    ptr, ids, tup = tr.csr(0, tr.max_user + 1)
+    u, i = tr.tuples()
+    # rows list (item, tuple index) in file order
+    assert np.all(np.diff(tup[ptr[5]:ptr[6]]) > 0)
+    assert np.array_equal(i[tup], ids)
+    assert np.array_equal(u[tup], np.repeat(np.arange(tr.max_user + 1), np.diff(ptr)))
+
+
+CASES = {
+    # reference test settings: tests/ials_test.cc:17-24, safer2_test.cc:12-86, erm_mf_test.cc, cvar_mf_test.cc,
+    # ialspp_test.cc:64, safer2pp_test.cc
+    "ials": (10, dict(uobs_weight=0.1, reg=0.003)),
+    "ialspp": (10, dict(uobs_weight=0.1, reg=0.003, block_size=4)),
+    "erm_mf": (10, dict(uobs_weight=0.004, reg=0.005)),
+    "cvar_mf": (50, dict(uobs_weight=0.008, reg=0.002, stepsize=0.4)),
+    "safer2": (10, dict(uobs_weight=0.004, reg=0.004, bandwidth=0.15)),
+    "safer2_snr": (10, dict(uobs_weight=0.004, reg=0.004, bandwidth=0.15, use_snr=1, sampling_ratio=0.5)),
+    "safer2_ep": (10, dict(uobs_weight=0.004, reg=0.004, bandwidth=0.7, use_epanechnikov=1)),
+    "safer2pp": (10, dict(uobs_weight=0.004, reg=0.004, bandwidth=0.15, block_size=4)),
+    "safer2pp_snr": (10, dict(uobs_weight=0.004, reg=0.004, bandwidth=0.15, block_size=4, use_snr=1, sampling_ratio=0.5)),
+    "safer2pp_ep": (10, dict(uobs_weight=0.004, reg=0.004, bandwidth=0.7, block_size=4, use_epanechnikov=1)),
+}
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_reference_thresholds(data, case):
+    """EXPECT_LE(0.2, mean NDCG@20) (tests/ials_test.cc:45 ...) and
+    EXPECT_NEAR(alpha, GetMeanWeight(), 0.02) after every epoch (tests/safer2_test.cc:135)."""
+    tr, vtr, vte = data
+    epochs, cfg = CASES[case]
+    name = case if case in O.MODEL_IDS else case.rsplit("_", 1)[0]
+    m = O.Model(tr.max_user + 1, tr.max_item + 1, init_seed=1, model=name, dim=8, **cfg)
+    m.initialize(tr)
+    for _ in range(epochs):
+        m.train(tr)
+        if name in ("safer2", "safer2pp"):
+            assert abs(m.state()["mean_weight"] - 0.3) <= 0.02
+    ev = m.evaluate(vtr, vte)
+    assert ev["ndcg"][:, 2].mean() >= 0.2
+    golden = json.load(open(os.path.join(helpers.GOLDEN, "oracle_fixture_golden.json")))
+    g = golden[case]
+    assert abs(ev["ndcg"][:, 2].mean() - g["ndcg20"]) < 2e-3
+    assert abs(ev["recall"][:, 2].mean() - g["recall20"]) < 2e-3
+    assert abs(m.state()["xi"] - g["xi"]) < 2e-3
+
+
+def test_stale_tail_quirk_is_load_bearing(data):
+    """B-1: 848 fixture items have n > 128 and n % 128 != 0."""
+    tr, _, _ = data
+    ptr, _, _ = tr.csr(1, tr.max_item + 1)
+    n = np.diff(ptr)
+    sel = (n > 128) & (n % 128 != 0)
+    assert int(sel.sum()) == 848
+    k = n[sel] // 128
+    assert int((128 - n[sel] % 128).sum()) == 61228
+
+
+def test_metric_cvar_matches_definition():
+    ms = np.array([0.5, 0.1, 0.9, 0.3, 0.7, 0.2, 0.4, 0.6, 0.8, 1.0], np.float32)
+    out = O.metric_cvar(ms, [0.1, 0.5])
+    s = np.sort(ms)
+    assert abs(out[0] - s[:2].mean()) < 1e-6   # pos = int(10*0.1)=1 -> mean of first 2
+    assert abs(out[1] - s[:6].mean()) < 1e-6
+
+
+def test_snr_indices_follow_libstdcxx(data):
+    tr, _, _ = data
+    m = O.Model(tr.max_user + 1, tr.max_item + 1, init_seed=1, model="safer2", dim=8, use_snr=1,
+                sampling_ratio=0.5, snr_seed=123, bandwidth=0.15, uobs_weight=0.004, reg=0.004)
+    m.initialize(tr)
+    idx = m.last_snr()
+    assert idx.shape == (5, 2017)  # (int)(4034 * 0.5f)
+    assert idx.min() >= 0 and idx.max() <= 4033
+    golden = json.load(open(os.path.join(helpers.GOLDEN, "oracle_fixture_golden.json")))
+    assert idx[0, :8].tolist() == golden["snr_first8_seed123"]
