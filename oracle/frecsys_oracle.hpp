@@ -327,17 +327,11 @@ struct Config {
 // Recommender::init_matrix (recommender.h:61-67): one mt19937, a fresh
 // normal_distribution<float>(0, stdev/sqrt(d)) per matrix, U first then V
 // (safer2.h:50-54).  The reference seeds from random_device; we inject.
+// Defined in oracle_rng.cc, which is compiled WITHOUT -march=native /
+// fp-contraction so that the float stream is the plain IEEE one on every host.
+void InitFactorsRaw(float* U, size_t nU, float* V, size_t nV, int dim, float stdev, unsigned seed);
 inline void InitFactors(Mat* U, Mat* V, float stdev, unsigned seed) {
-  const float adjusted = stdev / std::sqrt((double)U->cols);  // float / double sqrt(int), safer2.h:50
-  std::mt19937 gen{seed};
-  {
-    std::normal_distribution<float> d(0, adjusted);
-    for (auto& x : U->a) x = d(gen);
-  }
-  {
-    std::normal_distribution<float> d(0, adjusted);
-    for (auto& x : V->a) x = d(gen);
-  }
+  InitFactorsRaw(U->a.data(), U->a.size(), V->a.data(), V->a.size(), U->cols, stdev, seed);
 }
 
 // Kernel functions, safer2.h:599-647 (dup. safer2pp.h:705-754).  Arguments and

@@ -62,7 +62,7 @@ def build(force=False):
     .so is rebuilt when the host CPU differs from the one it was built on, so a
     library built in the dev container is never run with foreign -march code."""
     sig = _cpu_sig()
-    srcs = [os.path.join(HERE, f) for f in ("oracle_capi.cc", "frecsys_oracle.hpp", "Makefile")]
+    srcs = [os.path.join(HERE, f) for f in ("oracle_capi.cc", "oracle_rng.cc", "frecsys_oracle.hpp", "Makefile")]
     newest = max(os.path.getmtime(s) for s in srcs)
     ok = (os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == sig
           and os.path.getmtime(LIB) >= newest)
