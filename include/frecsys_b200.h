@@ -100,6 +100,10 @@ int frx_model_init_factors(frx_model* m, unsigned seed);
  * constructors do (safer2.h:55-59). */
 int frx_model_set_factors(frx_model* m, const float* U, const float* V);
 int frx_model_get_factors(frx_model* m, float* U, float* V);
+/* Overwrite the factors WITHOUT touching the per-user state (asynchronous: the host
+ * buffers must stay valid until frx_context_sync; use pinned memory).  This is the
+ * per-epoch host->device leg of a caller that keeps its factors in host memory. */
+int frx_model_upload_factors(frx_model* m, const float* U, const float* V);
 /* Initialize(const Dataset&) — safer2.h:819-838, safer2pp.h, erm_mf.h:573-587,
  * cvar_mf.h:710-726; a no-op for iALS / iALS++ (run_model.cc:246-257). */
 int frx_model_initialize(frx_model* m, frx_dataset* train);

@@ -21,7 +21,7 @@ EXPORTS = [
     "frx_last_error", "frx_context_create", "frx_context_destroy", "frx_context_sync",
     "frx_context_stream", "frx_comm_unique_id", "frx_context_init_comm", "frx_dataset_create",
     "frx_dataset_destroy", "frx_dataset_info", "frx_dataset_get_csr", "frx_model_create",
-    "frx_model_destroy", "frx_model_init_factors", "frx_model_set_factors", "frx_model_get_factors",
+    "frx_model_destroy", "frx_model_init_factors", "frx_model_set_factors", "frx_model_get_factors", "frx_model_upload_factors",
     "frx_model_initialize", "frx_model_train", "frx_model_stage", "frx_model_get_state",
     "frx_model_set_state", "frx_model_compute_stats", "frx_model_last_snr", "frx_model_evaluate",
     "frx_context_launch_count", "frx_context_set_profiling", "frx_context_stage_times", "frx_gramian",
@@ -102,6 +102,7 @@ def lib():
     L.frx_model_init_factors.argtypes = [vp, C.c_uint]
     L.frx_model_set_factors.argtypes = [vp, fp, fp]
     L.frx_model_get_factors.argtypes = [vp, fp, fp]
+    L.frx_model_upload_factors.argtypes = [vp, fp, fp]
     L.frx_model_initialize.argtypes = [vp, vp]
     L.frx_model_train.argtypes = [vp, vp]
     L.frx_model_stage.argtypes = [vp, vp, C.c_int]
@@ -237,9 +238,10 @@ class Model:
         _check(lib().frx_model_set_factors(self.h, _fp(U), _fp(V)))
         self.ctx.sync()
 
-    def set_factors_async(self, U, V):
-        """U, V must stay alive (ideally pinned) until the context is synchronised."""
-        _check(lib().frx_model_set_factors(self.h, _fp(U), _fp(V)))
+    def upload_factors(self, U, V):
+        """Overwrite factors only (state untouched), asynchronously; U, V must stay alive
+        (ideally pinned) until the context is synchronised."""
+        _check(lib().frx_model_upload_factors(self.h, _fp(U), _fp(V)))
 
     def factors(self, U=None, V=None):
         U = np.zeros((self.num_users, self.dim), np.float32) if U is None else U

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 #include <string>
@@ -456,6 +457,15 @@ extern "C" int frx_model_set_factors(frx_model* m, const float* U, const float* 
   return reset_state(m);
 }
 
+extern "C" int frx_model_upload_factors(frx_model* m, const float* U, const float* V) {
+  frx_context* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  const size_t d = m->cfg.dim;
+  if (U) CK(cudaMemcpyAsync(m->U, U, sizeof(float) * m->num_users * d, cudaMemcpyHostToDevice, c->stream));
+  if (V) CK(cudaMemcpyAsync(m->V, V, sizeof(float) * m->num_items * d, cudaMemcpyHostToDevice, c->stream));
+  return FRX_OK;
+}
+
 extern "C" int frx_model_init_factors(frx_model* m, unsigned seed) {
   // Recommender::init_matrix, recommender.h:61-67; order U then V, safer2.h:50-54.
   const size_t d = m->cfg.dim;
@@ -524,6 +534,12 @@ static int run_rows(frx_model* m, const RowCall& rc_) {
   p.uw = m->cfg.uobs_weight; p.reg = m->cfg.reg; p.reg_exp = m->cfg.reg_exp; p.alpha = m->cfg.alpha;
   p.stepsize = m->cfg.stepsize; p.num_users_total = m->num_users;
   p.status = c->status_dev;
+  static const bool disable_tc = getenv("FRX_DISABLE_TC") != nullptr;
+  if (!disable_tc && row_solve_tc_supported(p)) {
+    launch_row_solve_tc(p, c->stream, c->num_sms, &c->launches);
+    CK(cudaGetLastError());
+    return FRX_OK;
+  }
   const size_t per = row_solve_generic_scratch_floats(p.bd);
   if (per) {
     const int g = row_solve_generic_grid(p.num_rows, c->num_sms);

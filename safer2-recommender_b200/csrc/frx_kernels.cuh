@@ -54,6 +54,10 @@ void launch_row_solve_generic(const RowParams& p, cudaStream_t s, int num_sms, l
 size_t row_solve_generic_scratch_floats(int bd);  // per-CTA scratch (0 if shared memory suffices)
 int row_solve_generic_grid(int num_rows, int num_sms);
 
+// tcgen05 / TMEM path (frx_row_tc.cu): full-dimension solves with d = 128 or 256.
+bool row_solve_tc_supported(const RowParams& p);
+void launch_row_solve_tc(const RowParams& p, cudaStream_t s, int num_sms, long long* launches);
+
 // out[bd x fd] = sum_r w[r] * E[r][cs+i] * E[r][fs+j]; two-stage, deterministic.
 void launch_gramian(const float* E, int n, int d, int cs, int bd, int fs, int fd, const float* w,
                     float* out, int ld_out, float* workspace, size_t workspace_floats,

@@ -14,8 +14,8 @@
 namespace frx {
 
 namespace {
-constexpr int NT = 256;   // threads per CTA
-constexpr int NW = NT / 32;
+constexpr int NT_MAX = 1024;  // max threads per CTA
+
 constexpr int CH = 32;    // history entries staged per chunk
 
 __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
@@ -44,7 +44,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 template <bool VEC4>
-__global__ void __launch_bounds__(NT) row_solve_generic_kernel(RowParams p) {
+__global__ void __launch_bounds__(NT_MAX) row_solve_generic_kernel(RowParams p) {
+  const int NT = blockDim.x, NW = NT >> 5;
   extern __shared__ __align__(16) float smem[];
   const int bd = p.bd, d = p.d, cs = p.cs, mode = p.mode;
   const SmemLayout L(bd, d);
@@ -321,11 +322,13 @@ void launch_row_solve_generic(const RowParams& p_in, cudaStream_t s, int num_sms
   p.use_smem_matrix = fits ? 1 : 0;
   const size_t smem = smem_bytes_for(p.bd, p.d, fits);
   int per_sm = (int)((size_t)(224 * 1024) / (smem + 1024));
+  if (p.bd >= 96) per_sm = per_sm > 2 ? 2 : per_sm;
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 4) per_sm = 4;
   int grid = num_sms * per_sm;
   if (grid > p.num_rows) grid = p.num_rows;
   const bool vec4 = (p.d % 4 == 0) && (p.cs % 4 == 0) && (p.bd % 4 == 0);
+  const int NT = p.bd >= 96 ? 1024 : 256;  // large systems are latency-bound: more warps per SM
   if (vec4) {
     cudaFuncSetAttribute(row_solve_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     row_solve_generic_kernel<true><<<grid, NT, smem, s>>>(p);
