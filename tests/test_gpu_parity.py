@@ -251,3 +251,37 @@ def test_fixture_train_and_evaluate(pkg, O, ctx, name, cfg):
     for t in (tr, vtr, vte):
         t.close()
     m.close()
+
+
+@pytest.mark.parametrize("d", [128, 256])
+@pytest.mark.parametrize("name,cfg", [
+    ("ials", dict(uobs_weight=0.1, reg=0.003)),
+    ("safer2", dict(uobs_weight=0.004, reg=0.004, bandwidth=0.15)),
+    ("erm_mf", dict(uobs_weight=0.004, reg=0.005)),
+])
+def test_tensor_core_row_kernel_epoch(pkg, O, ctx, name, cfg, d):
+    """d = 128 / 256 take the tcgen05 path (3xTF32 SYRK in TMEM): one epoch must still agree
+    with the fp32 oracle to <= 1e-4 relative Frobenius; histories cover n = 1, 31, 32, 33, 128,
+    129, 255, 256, 300 (tile boundaries of the 32-entry operand tiles and the stale-tail quirk)."""
+    nu, ni = 300, 400
+    users, items = helpers.synth_tuples(
+        nu, ni, 30, seed=33, heavy_rows=[(0, 1), (1, 31), (2, 32), (3, 33), (4, 128), (5, 129), (6, 255), (8, 256), (9, 300)],
+        empty_users=(7,), empty_items=(11,))
+    ods, om, ds, m = make_pair(pkg, O, ctx, users, items, nu, ni, model=name, dim=d, **cfg)
+    om.initialize(ods)
+    m.initialize(ds)
+    om.train(ods)
+    m.train(ds)
+    U, V = m.factors()
+    Uo, Vo = om.factors()
+    so, sg = om.state(), m.state()
+    assert rel_fro(U, Uo) < FACTOR_TOL, rel_fro(U, Uo)
+    assert rel_fro(V, Vo) < FACTOR_TOL, rel_fro(V, Vo)
+    # per-row check as well: no single row may be far off
+    rowerr = np.linalg.norm(U - Uo, axis=1) / np.maximum(np.linalg.norm(Uo, axis=1), 1e-12)
+    assert rowerr.max() < 1e-3, (int(rowerr.argmax()), float(rowerr.max()))
+    np.testing.assert_allclose(sg["loss"], so["loss"], rtol=2e-4, atol=1e-6)
+    if name == "safer2":
+        assert abs(sg["xi"] - so["xi"]) < 1e-4
+    m.close()
+    ds.close()
