@@ -536,8 +536,26 @@ static int run_rows(frx_model* m, const RowCall& rc_) {
   p.status = c->status_dev;
   static const bool disable_tc = getenv("FRX_DISABLE_TC") != nullptr;
   if (!disable_tc && row_solve_tc_supported(p)) {
+    static const bool tc_debug = getenv("FRX_TC_DEBUG") != nullptr;
+    unsigned long long* dbg = nullptr;
+    if (tc_debug) {
+      CK(cudaMalloc(&dbg, 16 * sizeof(unsigned long long)));
+      CK(cudaMemsetAsync(dbg, 0, 16 * sizeof(unsigned long long), c->stream));
+      p.dbg = dbg;
+    }
     launch_row_solve_tc(p, c->stream, c->num_sms, &c->launches);
     CK(cudaGetLastError());
+    if (tc_debug) {
+      unsigned long long h[16];
+      CK(cudaMemcpyAsync(h, dbg, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      cudaFree(dbg);
+      const double rows = h[6] ? (double)h[6] : 1.0;
+      fprintf(stderr, "[frx tc] mode=%d rows=%llu cycles/row: gather+syrk=%.0f assemble=%.0f upd_wait=%.0f diag=%.0f trsm+tiles=%.0f backsub=%.0f\n",
+              p.mode, h[6], h[0] / rows, h[1] / rows, h[2] / rows, h[3] / rows, h[4] / rows, h[5] / rows);
+      fprintf(stderr, "[frx tc]   last row-warp per row: trsm=%.0f lst_store=%.0f opnd_store=%.0f fence+barrier=%.0f\n",
+              h[8] / rows, h[9] / rows, h[10] / rows, h[11] / rows);
+    }
     return FRX_OK;
   }
   const size_t per = row_solve_generic_scratch_floats(p.bd);

@@ -48,6 +48,7 @@ struct RowParams {
   size_t scratch_stride;
   int use_smem_matrix;
   int* status;  // set non-zero on a non-positive pivot
+  unsigned long long* dbg;  // optional per-phase cycle counters (FRX_TC_DEBUG), else null
 };
 
 void launch_row_solve_generic(const RowParams& p, cudaStream_t s, int num_sms, long long* launches);

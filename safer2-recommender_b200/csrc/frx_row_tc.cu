@@ -1,6 +1,6 @@
 // Fused row kernel on 5th-generation tensor cores (tcgen05 + TMEM), D = 128 / 256.
 //
-// One CTA per row r of the side being solved:
+// One CTA per row r of the side being solved; the d x d system never leaves the SM:
 //   phase A  A_r = sum_c s_c e_c e_c^T  (+ rhs = sum_c q_c e_c)
 //            16 loader warps gather the history rows (lane = history entry, 128 B per lane
 //            per load), split each fp32 into tf32 hi + lo and store them TRANSPOSED into
@@ -8,14 +8,20 @@
 //            tcgen05.mma kind::tf32 for hi*hi + hi*lo + lo*hi (error-compensated 3xTF32:
 //            fp32-level accuracy) into TMEM accumulators; lower-triangle tiles only.
 //            Two operand stages, mbarrier full/empty pipeline, tcgen05.commit frees a stage.
-//   phase B  TMEM -> packed lower triangle in shared memory -> M = a*A + b*G + reg*I ->
-//            Cholesky of the augmented system [M; rhs^T] -> back substitution -> row of X.
+//   phase B  in TMEM: M = a*A + b*G + reg*I, then a right-looking blocked Cholesky with
+//            32-wide panels.  Thread i owns matrix row i (tcgen05.ld gives it its 32 panel
+//            entries): the diagonal 32x32 block is factored by one warp with shuffles and
+//            inverted; the rows below do the triangular solve in registers; the L panel is
+//            written (tf32 hi/lo) as K-major operand tiles and the trailing update
+//            A22 -= L21 L21^T runs on the tensor cores with the a_negate bit.  The forward
+//            substitution is fused into the sweep; the back substitution uses the L panels
+//            kept in shared memory.
 //
 // Hardware conventions were established with tools/tc_probe.cu on a B200:
 //  * kind::tf32 works with K-major operands (SWIZZLE_128B, SBO = 1024 B, K step = +32 B on
 //    the descriptor start address); MN-major tf32 operands produce zeros, hence the transpose.
 //  * the MMA ignores the low 13 mantissa bits of fp32 inputs (truncation).
-//  * tcgen05.ld 32x32b: warp w reads TMEM lanes 32*(w%4)..+31, thread = accumulator row.
+//  * tcgen05.ld/st 32x32b: warp w touches TMEM lanes 32*(w%4)..+31, thread = accumulator row.
 // Restates ials.h:88-144, safer2.h:104-163 and safer2.h:166-221 (incl. the stale-tail quirk).
 #include "frx_kernels.cuh"
 #include <cstdint>
@@ -24,11 +30,10 @@ namespace frx {
 
 namespace {
 
-constexpr int TC_LOADER_WARPS = 16;                 // 2 groups of 8
+constexpr int TC_LOADER_WARPS = 16;                     // 2 groups of 8
 constexpr int TC_THREADS = (TC_LOADER_WARPS + 1) * 32;  // + 1 MMA-issuing warp
-constexpr int KT = 32;                              // history entries per operand tile (128 B rows)
+constexpr int KT = 32;                                  // entries per operand tile (128 B rows) = panel width
 
-__device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -61,6 +66,29 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+#define FRX_TMEM_LD32(u, taddr)                                                                                         \
+  asm volatile(                                                                                                         \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                         \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29," \
+      "%30,%31}, [%32];"                                                                                                \
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),     \
+        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),          \
+        "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),         \
+        "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])                       \
+      : "r"(taddr));                                                                                                    \
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
+
+#define FRX_TMEM_ST32(taddr, u)                                                                                         \
+  asm volatile(                                                                                                         \
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                                   \
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30," \
+      "%31,%32};" ::"r"(taddr),                                                                                         \
+      "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]), "r"(u[8]), "r"(u[9]),     \
+      "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15]), "r"(u[16]), "r"(u[17]), "r"(u[18]),       \
+      "r"(u[19]), "r"(u[20]), "r"(u[21]), "r"(u[22]), "r"(u[23]), "r"(u[24]), "r"(u[25]), "r"(u[26]), "r"(u[27]),       \
+      "r"(u[28]), "r"(u[29]), "r"(u[30]), "r"(u[31])                                                                    \
+      : "memory")
+
 // K-major SWIZZLE_128B smem descriptor: LBO unused (encoded 1), SBO = 1024 B, version 1.
 __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -71,15 +99,14 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// kind::tf32, fp32 accumulate, K-major A and B, M = 128.
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// kind::tf32, fp32 accumulate, K-major A and B, M = 128; optional negation of A.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int N, int a_negate = 0) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_negate & 1) << 13) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(128 >> 4) << 24);
 }
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+// byte offset of element (row mn, k-chunk c of 4 floats) in a K-major SWIZZLE_128B tile with 128 B rows
+__device__ __forceinline__ uint32_t tile_chunk_off(int mn, int c) {
+  return ((uint32_t)(mn >> 3) << 10) + ((uint32_t)(mn & 7) << 7) + ((((uint32_t)c ^ (uint32_t)(mn & 7)) & 7u) << 4);
 }
 
 // Column sums over the 32 lanes of C per-lane values; on return v[0] of lane l holds the sum
@@ -108,45 +135,51 @@ __device__ __forceinline__ void transpose_reduce(float (&v)[C], int lane) {
 
 template <int D>
 struct TcLayout {
-  static constexpr int kTileBytes = D * 128;             // one operand tile: D rows x 128 B
-  static constexpr int kStageBytes = 2 * kTileBytes;     // hi + lo
-  static constexpr int kStagingBytes = 2 * kStageBytes;  // two stages
-  static constexpr int kTriFloats = ((D + 1) * (D + 2)) / 2;
-  static constexpr int kMtxBytes = ((kTriFloats * 4 + 1023) / 1024) * 1024;
-  static constexpr int kBigBytes = kStagingBytes > kMtxBytes ? kStagingBytes : kMtxBytes;  // aliased region
-  // after the aliased region: rhs partials [2][D], colk [D+4], ldiag [D], sol [D], barriers
-  static constexpr int kRhsOff = kBigBytes;
-  static constexpr int kColkOff = kRhsOff + 2 * D * 4;
-  static constexpr int kLdiagOff = kColkOff + (D + 4) * 4;
-  static constexpr int kSolOff = kLdiagOff + D * 4;
-  static constexpr int kBarOff = kSolOff + D * 4;
+  static constexpr int P = D / 32;                        // panels
+  static constexpr int kTileBytes = D * 128;              // one operand tile: D rows x 128 B
+  static constexpr int kStageBytes = 2 * kTileBytes;      // hi + lo
+  static constexpr int kStagingBytes = 2 * kStageBytes;   // phase A: two stages
+  // phase B (aliased with the staging area): L-panel operand tiles (hi, lo) + fp32 L panels
+  static constexpr int kLstFloats = 32 * (P * D - 16 * P * (P - 1));  // sum_p 32*(D-32p)
+  static constexpr int kLstOff = kStageBytes;
+  static constexpr int kPhaseB = kLstOff + kLstFloats * 4;
+  static constexpr int kBigBytes = kStagingBytes > kPhaseB ? kStagingBytes : kPhaseB;
+  static constexpr int kRhsOff = kBigBytes;               // rhs partials [2][D]
+  static constexpr int kLdOff = kRhsOff + 2 * D * 4;      // diagonal block scratch [32][33]
+  static constexpr int kWsumOff = kLdOff + 32 * 33 * 4;   // per-warp column sums [P][32]
+  static constexpr int kYOff = kWsumOff + P * 32 * 4;     // y of the current panel [32]
+  static constexpr int kBarOff = ((kYOff + 32 * 4 + 15) / 16) * 16;
   static constexpr int kTotal = kBarOff + 64;
   static constexpr int kTmemCols = D == 256 ? 512 : 128;
+  __host__ __device__ static constexpr int lst_off(int p) { return 32 * (p * D - 16 * p * (p - 1)); }
 };
 
 template <int D>
 __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p) {
   using L = TcLayout<D>;
-  constexpr int F4 = D / 32;   // float4 loads per loader lane (its 128 B / 64 B slab of the gathered row)
+  constexpr int P = L::P;
+  constexpr int F4 = D / 32;   // float4 loads per loader lane
   constexpr int C = 4 * F4;    // floats per loader lane
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  float* Mtx = reinterpret_cast<float*>(sm);
+  uint8_t* opnd_hi = sm;                      // phase B operand tiles (alias stage 0)
+  uint8_t* opnd_lo = sm + L::kTileBytes;
+  float* Lst = reinterpret_cast<float*>(sm + L::kLstOff);
   float* rhs_part = reinterpret_cast<float*>(sm + L::kRhsOff);
-  float* colk = reinterpret_cast<float*>(sm + L::kColkOff);
-  float* ldiag = reinterpret_cast<float*>(sm + L::kLdiagOff);
-  float* sol = reinterpret_cast<float*>(sm + L::kSolOff);
+  float* Ld = reinterpret_cast<float*>(sm + L::kLdOff);
+  float* wsum = reinterpret_cast<float*>(sm + L::kWsumOff);
+  float* yS = reinterpret_cast<float*>(sm + L::kYOff);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::kBarOff);
   uint64_t* full_bar = bars;       // [2]
   uint64_t* empty_bar = bars + 2;  // [2]
-  uint64_t* acc_bar = bars + 4;    // [1]
+  uint64_t* acc_bar = bars + 4;    // [1] SYRK accumulators complete
+  uint64_t* upd_bar = bars + 5;    // [1] trailing update complete
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int NT = TC_THREADS, NW = TC_THREADS / 32;
   const int mode = p.mode;
   const bool item_side = (mode == RM_SAFER_V);
-  float* rhs = Mtx + tri(D);
+  const bool is_row_warp = warp < P;   // warp w owns matrix rows 32w .. 32w+31
 
   if (tid == 0) {
     mbar_init(&full_bar[0], 8);
@@ -154,6 +187,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
     mbar_init(&empty_bar[0], 1);
     mbar_init(&empty_bar[1], 1);
     mbar_init(acc_bar, 1);
+    mbar_init(upd_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == TC_LOADER_WARPS) {
@@ -165,10 +199,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   const uint32_t sm_addr = smem_u32(sm);
+  // TMEM address of (row of this thread's lane quarter, column 0) for the M block this warp belongs to
+  const int rq = warp & 3, rb = (D == 256) ? ((warp >> 2) & 1) : 0;
+  const uint32_t trow = tmem_base + ((uint32_t)(32 * rq) << 16) + (rb ? 256u : 0u);
 
   uint32_t loader_use = 0;          // tiles this loader group has staged so far (all rows)
   uint32_t mma_use[2] = {0u, 0u};   // tiles consumed per stage (all rows)
   uint32_t row_count = 0;
+  uint32_t upd_count = 0;           // trailing-update commits so far (all rows)
+  unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tstamp = clock64();
+#define FRX_DBG_LAP(slot) do { if (p.dbg && tid == 0) { const long long now_ = clock64(); dbg_acc[slot] += (unsigned long long)(now_ - tstamp); tstamp = now_; } } while (0)
 
   for (int ri = blockIdx.x; ri < p.num_rows; ri += gridDim.x, ++row_count) {
     const int r = p.order[ri];
@@ -221,8 +262,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
             const float x = x4[t4];
             const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
             const float lo = x - hi;
-            const uint32_t off = ((uint32_t)(mn >> 3) << 10) + ((uint32_t)(mn & 7) << 7) +
-                                 (((kq ^ (uint32_t)(mn & 7)) & 7u) << 4) + kr;
+            const uint32_t off = tile_chunk_off(mn, (int)kq) + kr;
             *reinterpret_cast<float*>(hi_tile + off) = hi;
             *reinterpret_cast<float*>(lo_tile + off) = lo;
             rv[4 * j + t4] = qr * x;
@@ -237,7 +277,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
       }
       if (C == 32 || (lane & 1) == 0) rhs_part[g * D + slab + (C == 32 ? lane : (lane >> 1))] = rhs_acc;
     } else {
-      // ================= MMA issuer =================
+      // ================= MMA issuer: SYRK =================
       constexpr uint32_t idesc_n128 = make_idesc_tf32(128);
       constexpr uint32_t idesc_n256 = make_idesc_tf32(256);
       for (int t = 0; t < T; ++t) {
@@ -255,10 +295,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
             const uint64_t b_lo = make_kmajor_desc(lo_addr + ko);
             const uint32_t first = (t == 0 && ks == 0) ? 0u : 1u;
             {  // rows 0..127 x cols 0..127 -> TMEM columns [0,128)
-              const uint64_t a_hi = b_hi, a_lo = b_lo;
-              umma_tf32(tmem_base, a_hi, b_hi, idesc_n128, first);
-              umma_tf32(tmem_base, a_hi, b_lo, idesc_n128, 1u);
-              umma_tf32(tmem_base, a_lo, b_hi, idesc_n128, 1u);
+              umma_tf32(tmem_base, b_hi, b_hi, idesc_n128, first);
+              umma_tf32(tmem_base, b_hi, b_lo, idesc_n128, 1u);
+              umma_tf32(tmem_base, b_lo, b_hi, idesc_n128, 1u);
             }
             if (D == 256) {  // rows 128..255 x cols 0..255 -> TMEM columns [256,512)
               const uint64_t a_hi = make_kmajor_desc(hi_addr + 128 * 128 + ko);
@@ -275,39 +314,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
       }
     }
 
-    // ================= phase B: everyone =================
+    // ================= phase B =================
     mbar_wait(acc_bar, row_count & 1);
     tc_fence_after();
-    __syncthreads();  // rhs_part visible; all operand tiles consumed -> the staging area may be overwritten
-    if (warp < 16) {
-      // TMEM -> packed lower triangle.  warp w: lane quarter w%4, M block (w/4)%2, column chunks of parity w/8.
-      const int q = warp & 3, b = (warp >> 2) & 1, par = warp >> 3;
-      if (D == 256 || b == 0) {
-        const int i = 128 * b + 32 * q + lane;
-        const uint32_t tbase = tmem_base + ((uint32_t)(32 * q) << 16) + (b ? 256u : 0u);
-        const int nchunks = (128 * b + 32 * q + 31) / 32 + 1;  // columns 0 .. 32*nchunks-1 cover j <= i for the whole warp
-        float* mrow = Mtx + tri(i);
-        for (int ch = par; ch < nchunks; ch += 2) {
-          uint32_t u[32];
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-              "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-              : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
-                "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
-                "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
-                "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
-              : "r"(tbase + (uint32_t)(32 * ch)));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
-            const int j = 32 * ch + jj;
-            if (j <= i) mrow[j] = __uint_as_float(u[jj]);
-          }
-        }
-      }
-    }
-    tc_fence_before();
-    __syncthreads();
+    __syncthreads();  // rhs_part visible; all operand tiles consumed -> the staging area may be reused
+    FRX_DBG_LAP(0);  // phase A (gather + SYRK)
 
     // ---- per-row scalars (same formulas as the generic kernel) ----
     float reg, weight = 1.f;
@@ -321,76 +332,281 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
     }
     const bool user_form = (mode == RM_SAFER_U);
     const float nf = (float)n;
-    for (int i = warp; i < D; i += NW) {
-      float* mrow = Mtx + tri(i);
-      const float* grow = p.G + (size_t)i * D;
-      for (int j = lane; j <= i; j += 32) {
-        const float g = __ldg(grow + j);
-        const float sij = mrow[j];
-        float m;
-        if (user_form) {
-          m = sij / nf;
-          m += p.uw * g;
-          m *= weight;
-          if (i == j) m += reg;
-        } else if (mode == RM_IALS) {
-          m = p.uw * g;
-          if (i == j) m += reg;
-          m += sij;
-        } else {
-          m = p.uw * g + sij;
-          if (i == j) m += reg;
+    const float inv_nf = 1.f / nf;
+
+    // ---- assemble M = a*A + b*G + reg*I in TMEM (lower part incl. the diagonal 32-blocks) ----
+    if (warp < 16 && (D == 256 || ((warp >> 2) & 1) == 0 || D == 128)) {
+      const int split = (D == 256) ? (warp >> 3) : (warp >> 2);
+      constexpr int nsplit = (D == 256) ? 2 : 4;
+      const int i = 128 * rb + 32 * rq + lane;
+      const int nch = 4 * rb + rq + 1;  // 32-column chunks covering j <= i for the whole warp
+      // G block [32 rows of this warp][32 columns] is fetched with coalesced 128 B row segments into a
+      // private, XOR-swizzled 4 KB buffer (the operand-tile area is idle here), then read row-per-lane.
+      float* gbuf = reinterpret_cast<float*>(sm) + warp * 1024;
+      const float* gblk = p.G + (size_t)(128 * rb + 32 * rq) * D;
+      for (int ch = split; ch < nch; ch += nsplit) {
+        uint32_t u[32];
+        FRX_TMEM_LD32(u, trow + (uint32_t)(32 * ch));
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int row = it * 4 + (lane >> 3), c16 = lane & 7;
+          const float4 gv = __ldg(reinterpret_cast<const float4*>(gblk + (size_t)row * D + 32 * ch) + c16);
+          *reinterpret_cast<float4*>(gbuf + row * 32 + ((c16 ^ (row & 7)) << 2)) = gv;
         }
-        mrow[j] = m;
+        __syncwarp();
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 gv = *reinterpret_cast<const float4*>(gbuf + lane * 32 + ((c4 ^ (lane & 7)) << 2));
+          const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+          for (int t4 = 0; t4 < 4; ++t4) {
+            const int jj = 4 * c4 + t4;
+            const int j = 32 * ch + jj;
+            const float sij = __uint_as_float(u[jj]);
+            float m;
+            if (user_form) {  // safer2.h:143-150
+              m = sij * inv_nf;  // reference divides (safer2.h:143); 1 ulp apart, far inside the tolerance
+              m += p.uw * gg[t4];
+              m *= weight;
+              if (i == j) m += reg;
+            } else if (mode == RM_IALS) {  // ials.h:101-105
+              m = p.uw * gg[t4];
+              if (i == j) m += reg;
+              m += sij;
+            } else {  // safer2.h:176,206-208
+              m = p.uw * gg[t4] + sij;
+              if (i == j) m += reg;
+            }
+            u[jj] = __float_as_uint(m);
+          }
+        }
+        FRX_TMEM_ST32(trow + (uint32_t)(32 * ch), u);
       }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
-    {
+    float b_reg = 0.f;  // this row-thread's rhs element, then y_i, then x_i
+    if (is_row_warp) {
+      const int i = 32 * warp + lane;
       const float sc = user_form ? weight / nf : 1.f;
-      for (int k = tid; k < D; k += NT) rhs[k] = (rhs_part[k] + rhs_part[D + k]) * sc;
-      if (tid == 0) rhs[D] = 0.f;
+      b_reg = (rhs_part[i] + rhs_part[D + i]) * sc;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    FRX_DBG_LAP(1);  // assemble
+
+    // ---- blocked Cholesky, 32-wide panels ----
+#pragma unroll 1
+    for (int pn = 0; pn < P; ++pn) {
+      const int c0 = 32 * pn, c1 = c0 + 32;
+      if (pn > 0) {  // trailing update of the previous panel has landed in TMEM
+        mbar_wait(upd_bar, (upd_count - 1) & 1);
+        tc_fence_after();
+      }
+      FRX_DBG_LAP(2);  // exposed wait for the trailing update
+      float a[32];
+      if (is_row_warp && warp >= pn) {
+        uint32_t u[32];
+        FRX_TMEM_LD32(u, trow + (uint32_t)c0);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(u[j]);
+      }
+      float* Lp = Lst + L::lst_off(pn);  // panel storage: row (i - c0) -> 32 floats; rows 0..31 hold inv(L11)
+      if (warp == pn) {
+        // -- diagonal block: Cholesky by shuffles (lane = row); 1/l_kk goes to shared memory --
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          float akk = __shfl_sync(0xffffffffu, a[k], k);
+          if (!(akk > 0.f)) {
+            if (lane == 0) atomicExch(p.status, 1);
+            akk = 1.f;
+          }
+          const float rs = rsqrtf(akk);
+          if (lane == k) wsum[k] = rs;
+          const float lk = a[k] * rs;
+          a[k] = lk;
+#pragma unroll
+          for (int j = k + 1; j < 32; ++j) {
+            const float lj = __shfl_sync(0xffffffffu, lk, j);
+            a[j] = fmaf(-lk, lj, a[j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j > lane) a[j] = 0.f;     // strict upper part of the block
+          Ld[lane * 33 + j] = a[j];
+        }
+        __syncwarp();
+        // -- inverse of L11 by columns: lane c solves L x = e_c (column sweep) --
+        float x[32];
+#pragma unroll
+        for (int i2 = 0; i2 < 32; ++i2) x[i2] = (i2 == lane) ? 1.f : 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          x[j] *= wsum[j];
+#pragma unroll
+          for (int i2 = j + 1; i2 < 32; ++i2) x[i2] = fmaf(-Ld[i2 * 33 + j], x[j], x[i2]);
+        }
+        // lane c holds column c of inv(L11): store as Lp[i][c]; y = inv(L11) * b via a transpose-reduce
+#pragma unroll
+        for (int i2 = 0; i2 < 32; ++i2) {
+          Lp[i2 * 32 + ((((lane >> 2) ^ (i2 & 7)) & 7) << 2) + (lane & 3)] = x[i2];
+          x[i2] *= b_reg;
+        }
+        transpose_reduce<32>(x, lane);
+        b_reg = x[0];  // y_i of this row
+        yS[lane] = b_reg;
+      }
+      __syncthreads();  // inv(L11) and y of the panel are visible
+      FRX_DBG_LAP(3);  // panel load + diagonal block factor / inverse
+      long long w7t = 0;
+      if (p.dbg && warp == P - 1 && lane == 0) w7t = clock64();
+      if (is_row_warp && warp > pn) {
+        // -- rows below: L21 row = a * inv(L11)^T (in place, descending k), then forward substitution --
+#pragma unroll
+        for (int k = 31; k >= 0; --k) {
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          const float4* lrow = reinterpret_cast<const float4*>(Lp + k * 32);
+#pragma unroll
+          for (int j4 = 0; j4 <= k / 4; ++j4) {
+            const float4 l4 = lrow[(j4 ^ (k & 7)) & 7];
+            s0 = fmaf(a[4 * j4], l4.x, s0);
+            if (4 * j4 + 1 <= k) s1 = fmaf(a[4 * j4 + 1], l4.y, s1);
+            if (4 * j4 + 2 <= k) s2 = fmaf(a[4 * j4 + 2], l4.z, s2);
+            if (4 * j4 + 3 <= k) s3 = fmaf(a[4 * j4 + 3], l4.w, s3);
+          }
+          const float s = (s0 + s1) + (s2 + s3);
+          a[k] = s;
+        }
+        float dot = 0.f;
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const float4 y4 = reinterpret_cast<const float4*>(yS)[k4];
+          dot = fmaf(a[4 * k4], y4.x, dot);
+          dot = fmaf(a[4 * k4 + 1], y4.y, dot);
+          dot = fmaf(a[4 * k4 + 2], y4.z, dot);
+          dot = fmaf(a[4 * k4 + 3], y4.w, dot);
+        }
+        b_reg -= dot;
+        if (p.dbg && warp == P - 1 && lane == 0) { const long long n_ = clock64(); atomicAdd(p.dbg + 8, (unsigned long long)(n_ - w7t)); w7t = n_; }
+        const int i = 32 * warp + lane;
+        float4* dst = reinterpret_cast<float4*>(Lp + (size_t)(i - c0) * 32);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4)
+          dst[(c4 ^ (lane & 7)) & 7] = make_float4(a[4 * c4], a[4 * c4 + 1], a[4 * c4 + 2], a[4 * c4 + 3]);
+        if (p.dbg && warp == P - 1 && lane == 0) { const long long n_ = clock64(); atomicAdd(p.dbg + 9, (unsigned long long)(n_ - w7t)); w7t = n_; }
+      }
+      if (c1 < D) {
+        if (is_row_warp && warp >= pn) {
+          // -- L panel rows as K-major tf32 hi/lo operand tiles --
+          const int i = 32 * warp + lane;
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            float hi[4], lo[4];
+#pragma unroll
+            for (int t4 = 0; t4 < 4; ++t4) {
+              const float x = a[4 * c4 + t4];
+              hi[t4] = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+              lo[t4] = x - hi[t4];
+            }
+            const uint32_t off = tile_chunk_off(i, c4);
+            *reinterpret_cast<float4*>(opnd_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(opnd_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+        if (p.dbg && warp == P - 1 && lane == 0) { const long long n_ = clock64(); atomicAdd(p.dbg + 10, (unsigned long long)(n_ - w7t)); w7t = n_; }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        __syncthreads();
+        if (p.dbg && warp == P - 1 && lane == 0) { const long long n_ = clock64(); atomicAdd(p.dbg + 11, (unsigned long long)(n_ - w7t)); w7t = n_; }
+        FRX_DBG_LAP(4);  // TRSM + operand tiles
+        if (warp == TC_LOADER_WARPS) {
+          tc_fence_after();
+          if (lane == 0) {
+            // A22 -= L21 L21^T on columns [c1, limit) of every M block that still has rows >= c1
+            const uint32_t hi_addr = sm_addr, lo_addr = sm_addr + L::kTileBytes;
+#pragma unroll
+            for (int ks = 0; ks < KT / 8; ++ks) {
+              const uint32_t ko = ks * 32;
+              const uint64_t b_hi = make_kmajor_desc(hi_addr + (uint32_t)c1 * 128 + ko);
+              const uint64_t b_lo = make_kmajor_desc(lo_addr + (uint32_t)c1 * 128 + ko);
+              if (c1 < 128) {
+                const uint32_t idesc = make_idesc_tf32(128 - c1, 1);
+                const uint64_t a_hi = make_kmajor_desc(hi_addr + ko), a_lo = make_kmajor_desc(lo_addr + ko);
+                umma_tf32(tmem_base + (uint32_t)c1, a_hi, b_hi, idesc, 1u);
+                umma_tf32(tmem_base + (uint32_t)c1, a_hi, b_lo, idesc, 1u);
+                umma_tf32(tmem_base + (uint32_t)c1, a_lo, b_hi, idesc, 1u);
+              }
+              if (D == 256) {
+                const uint32_t idesc = make_idesc_tf32(256 - c1, 1);
+                const uint64_t a_hi = make_kmajor_desc(hi_addr + 128 * 128 + ko);
+                const uint64_t a_lo = make_kmajor_desc(lo_addr + 128 * 128 + ko);
+                umma_tf32(tmem_base + 256 + (uint32_t)c1, a_hi, b_hi, idesc, 1u);
+                umma_tf32(tmem_base + 256 + (uint32_t)c1, a_hi, b_lo, idesc, 1u);
+                umma_tf32(tmem_base + 256 + (uint32_t)c1, a_lo, b_hi, idesc, 1u);
+              }
+            }
+            umma_commit(upd_bar);
+          }
+          __syncwarp();
+        }
+        ++upd_count;
+      }
     }
     __syncthreads();
 
-    // ---- Cholesky of the augmented system; row D carries rhs -> y ----
-    for (int k = 0; k < D; ++k) {
-      float pivot = Mtx[tri(k) + k];
-      if (!(pivot > 0.f)) {
-        if (tid == 0) atomicExch(p.status, 1);
-        pivot = 1.f;
+    // ---- back substitution L^T x = y, panel by panel from the bottom; b_reg: y_i -> x_i ----
+#pragma unroll 1
+    for (int pn = P - 1; pn >= 0; --pn) {
+      const int c0 = 32 * pn;
+      const float* Lp = Lst + L::lst_off(pn);
+      if (is_row_warp && warp > pn) {
+        const int i = 32 * warp + lane;
+        const float4* src = reinterpret_cast<const float4*>(Lp + (size_t)(i - c0) * 32);
+        float part[32];
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 l4 = src[(c4 ^ (lane & 7)) & 7];
+          part[4 * c4] = l4.x * b_reg;
+          part[4 * c4 + 1] = l4.y * b_reg;
+          part[4 * c4 + 2] = l4.z * b_reg;
+          part[4 * c4 + 3] = l4.w * b_reg;
+        }
+        transpose_reduce<32>(part, lane);
+        wsum[warp * 32 + lane] = part[0];
       }
-      const float l = sqrtf(pivot);
-      for (int i = k + 1 + tid; i <= D; i += NT) {
-        const float v = Mtx[tri(i) + k] / l;
-        Mtx[tri(i) + k] = v;
-        colk[i] = v;
-      }
-      if (tid == 0) ldiag[k] = l;
       __syncthreads();
-      for (int i = k + 1 + warp; i <= D; i += NW) {
-        const float lik = colk[i];
-        float* mrow = Mtx + tri(i);
-        const int jmax = min(i, D - 1);
-        for (int j = k + 1 + lane; j <= jmax; j += 32) mrow[j] = fmaf(-lik, colk[j], mrow[j]);
+      if (warp == pn) {
+        float rk = b_reg;
+        for (int w2 = pn + 1; w2 < P; ++w2) rk -= wsum[w2 * 32 + lane];
+        // x_k = sum_{j >= k} inv(L11)[j][k] * r_j: lane j scales row j of inv(L11), column sums by transpose-reduce
+        float pr[32];
+        const float4* lrow = reinterpret_cast<const float4*>(Lp + lane * 32);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 l4 = lrow[(c4 ^ (lane & 7)) & 7];
+          pr[4 * c4] = l4.x * rk;
+          pr[4 * c4 + 1] = l4.y * rk;
+          pr[4 * c4 + 2] = l4.z * rk;
+          pr[4 * c4 + 3] = l4.w * rk;
+        }
+        transpose_reduce<32>(pr, lane);
+        const float xk = pr[0];
+        b_reg = xk;
       }
       __syncthreads();
     }
-    if (warp == 0) {
-      for (int j = lane; j < D; j += 32) sol[j] = rhs[j];
-      __syncwarp();
-      for (int k = D - 1; k >= 0; --k) {
-        const float xk = sol[k] / ldiag[k];
-        __syncwarp();
-        if (lane == 0) sol[k] = xk;
-        const float* mrow = Mtx + tri(k);
-        for (int j = lane; j < k; j += 32) sol[j] = fmaf(-mrow[j], xk, sol[j]);
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    for (int k = tid; k < D; k += NT) p.X[(size_t)xr * D + k] = sol[k];
-    __syncthreads();  // Mtx (aliased with the operand stages) is free for the next row's loaders
+    if (is_row_warp) p.X[(size_t)xr * D + 32 * warp + lane] = b_reg;
+    tc_fence_before();
+    __syncthreads();  // the aliased shared memory and TMEM are free for the next row
+    FRX_DBG_LAP(5);  // back substitution + store
   }
 
+  if (p.dbg && tid == 0) {
+    for (int i = 0; i < 6; ++i) atomicAdd(p.dbg + i, dbg_acc[i]);
+    atomicAdd(p.dbg + 6, (unsigned long long)row_count);
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == TC_LOADER_WARPS)
@@ -414,7 +630,7 @@ void launch_row_solve_tc(const RowParams& p, cudaStream_t s, int num_sms, long l
   } else {
     const int smem = TcLayout<128>::kTotal + 1024;
     cudaFuncSetAttribute(row_solve_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    int grid = 2 * num_sms < p.num_rows ? 2 * num_sms : p.num_rows;
+    int grid = num_sms < p.num_rows ? num_sms : p.num_rows;
     row_solve_tc_kernel<128><<<grid, TC_THREADS, smem, s>>>(p);
   }
   if (launches) ++*launches;
