@@ -58,6 +58,7 @@ struct frx_context {
   std::vector<StageTimer> timers;
   size_t timers_used = 0;
   int rank = 0, world = 1;
+  long long collectives = 0;
 #ifdef FRX_WITH_NCCL
   ncclComm_t comm = nullptr;
 #endif
@@ -374,15 +375,70 @@ static int ensure_eval_maps(frx_dataset* d) {
 // ---------------------------------------------------------------------------
 // model
 // ---------------------------------------------------------------------------
+#ifdef FRX_WITH_NCCL
+#define NCK(call)                                                                                \
+  do {                                                                                           \
+    ncclResult_t r_ = (call);                                                                    \
+    if (r_ != ncclSuccess) return fail(FRX_ERR_COMM, "%s failed: %s", #call, ncclGetErrorString(r_)); \
+  } while (0)
+#endif
+
+// All-gather of row blocks: rank k owns rows [rank_begin[k], rank_begin[k+1]) of X (row_floats floats
+// each) and every rank ends with all of them (collectives C2/C3/C4).  In place, as one
+// group of NCCL broadcasts because the blocks are balanced on work, not on row count.
+static int allgather_rows(frx_context* c, float* X, size_t row_floats, const std::vector<int>& rank_begin) {
+  if (c->world <= 1) return FRX_OK;
+#ifdef FRX_WITH_NCCL
+  NCK(ncclGroupStart());
+  for (int k = 0; k < c->world; ++k) {
+    const size_t b = rank_begin[k], e = rank_begin[k + 1];
+    if (e > b) {
+      float* blk = X + b * row_floats;
+      NCK(ncclBroadcast(blk, blk, (e - b) * row_floats, ncclFloat, k, c->comm, c->stream));
+    }
+  }
+  NCK(ncclGroupEnd());
+  ++c->collectives;
+  return FRX_OK;
+#else
+  (void)X; (void)row_floats; (void)rank_begin;
+  return fail(FRX_ERR_COMM, "built without NCCL");
+#endif
+}
+
+// Sum of the per-rank partial Gramians (collective C1).
+static int allreduce_sum(frx_context* c, float* buf, size_t count) {
+  if (c->world <= 1) return FRX_OK;
+#ifdef FRX_WITH_NCCL
+  NCK(ncclAllReduce(buf, buf, count, ncclFloat, ncclSum, c->comm, c->stream));
+  ++c->collectives;
+  return FRX_OK;
+#else
+  (void)buf; (void)count;
+  return fail(FRX_ERR_COMM, "built without NCCL");
+#endif
+}
+
+// out[cs:cs+bd, fs:fs+fd] = E[:, cs:cs+bd]^T diag(w) E[:, fs:fs+fd].  With several ranks each one
+// contracts an even share of the rows and the d x d (or B x d) partials are all-reduced.
 static int gramian_into(frx_model* m, const float* E, int n, int cs, int bd, int fs, int fd,
                         const float* w, float* out) {
   frx_context* c = m->ctx;
   const int d = m->cfg.dim;
-  int rc = c->ensure_gram_ws(gramian_workspace_floats(n, bd, fd, c->num_sms));
+  int b = 0, e = n;
+  if (c->world > 1) {
+    b = (int)((long long)n * c->rank / c->world);
+    e = (int)((long long)n * (c->rank + 1) / c->world);
+  }
+  int rc = c->ensure_gram_ws(gramian_workspace_floats(e - b, bd, fd, c->num_sms));
   if (rc) return rc;
-  launch_gramian(E, n, d, cs, bd, fs, fd, w, out + (size_t)cs * d + fs, d, c->gram_ws, c->gram_ws_floats,
-                 c->stream, c->num_sms, &c->launches);
+  launch_gramian(E + (size_t)b * d, e - b, d, cs, bd, fs, fd, w ? w + b : nullptr, out + (size_t)cs * d + fs, d,
+                 c->gram_ws, c->gram_ws_floats, c->stream, c->num_sms, &c->launches);
   CK(cudaGetLastError());
+  if (c->world > 1) {
+    if (fs != 0 || fd != d) return fail(FRX_ERR_ARG, "sharded Gramian needs full-width strips");
+    return allreduce_sum(c, out + (size_t)cs * d, (size_t)bd * d);
+  }
   return FRX_OK;
 }
 
@@ -571,6 +627,15 @@ static int run_rows(frx_model* m, const RowCall& rc_) {
   return FRX_OK;
 }
 
+// Row solve on this rank's rows, then the all-gather that makes the updated factor block visible
+// to every rank before the next half-step.
+static int run_rows_sharded(frx_model* m, const RowCall& rc_) {
+  int rc = run_rows(m, rc_);
+  if (rc) return rc;
+  if (m->ctx->world > 1 && !rc_.xmap) return allgather_rows(m->ctx, rc_.X, (size_t)m->cfg.dim, rc_.rows->rank_begin);
+  return FRX_OK;
+}
+
 static int stage_item_gramian(frx_model* m) {
   m->ctx->stage_begin("gramian_V");
   int rc = gramian_into(m, m->V, m->num_items, 0, m->cfg.dim, 0, m->cfg.dim, nullptr, m->G);
@@ -589,9 +654,10 @@ static int stage_user_loss(frx_model* m, frx_dataset* ds, const float* G, const 
   p.beta = m->cfg.uobs_weight; p.halve = m->is_ials_family() ? 0 : 1;
   p.quad = m->quad; p.loss = m->loss;
   launch_user_loss(p, m->num_users, c->stream, c->num_sms, &c->launches);
-  c->stage_end();
   CK(cudaGetLastError());
-  return FRX_OK;
+  int rc = allgather_rows(c, m->loss, 1, ds->by_user.rank_begin);  // C4: every rank needs all losses for xi / z
+  c->stage_end();
+  return rc;
 }
 
 static int stage_weights(frx_model* m) {
@@ -682,7 +748,7 @@ static int stage_step_u(frx_model* m, frx_dataset* ds) {
   RowCall rc{&ds->by_user, m->V, m->num_items, m->U, nullptr, nullptr, m->G, nullptr, m->z,
              RM_SAFER_U, 0, m->cfg.dim, nullptr};
   if (m->cfg.model == FRX_CVAR_MF) rc.mode = RM_CVAR_U;
-  int r = run_rows(m, rc);
+  int r = run_rows_sharded(m, rc);
   m->ctx->stage_end();
   return r;
 }
@@ -699,7 +765,7 @@ static int stage_step_v(frx_model* m, frx_dataset* ds, const float* users) {
   RowCall rc{&ds->by_item, users, m->num_users, m->V, nullptr, nullptr, m->Gz, m->norm_w, nullptr,
              RM_SAFER_V, 0, m->cfg.dim, nullptr};
   if (m->cfg.model == FRX_CVAR_MF) rc.mode = RM_CVAR_V;
-  r = run_rows(m, rc);
+  r = run_rows_sharded(m, rc);
   c->stage_end();
   return r;
 }
@@ -717,7 +783,7 @@ static int stage_ials_step(frx_model* m, frx_dataset* ds, bool user_side, float*
   c->stage_begin(user_side ? "step_U" : "step_V");
   const Csr* rows = rows_override ? rows_override : (user_side ? &ds->by_user : &ds->by_item);
   RowCall rc{rows, other, n_other, X, nullptr, xmap, m->Gz, nullptr, nullptr, RM_IALS, 0, m->cfg.dim, nullptr};
-  r = run_rows(m, rc);
+  r = run_rows_sharded(m, rc);
   c->stage_end();
   return r;
 }
@@ -784,6 +850,8 @@ extern "C" int frx_model_train(frx_model* m, frx_dataset* ds) {
     return fail(FRX_ERR_ARG, "dataset ids exceed the model's num_users/num_items");
   c->timers_used = 0;
   const int d = m->cfg.dim, B = m->cfg.block_size;
+  if (c->world > 1 && m->is_pp())
+    return fail(FRX_ERR_ARG, "iALS++ / SAFER2++ are single-GPU in this build (the tuple-indexed prediction cache is not sharded)");
   switch (m->cfg.model) {
     case FRX_IALS:  // ials.h:187-224
       RC(stage_ials_step(m, ds, true, m->U, nullptr, nullptr));

@@ -2,6 +2,8 @@
 identical inputs and initial factors.  Tolerances are BASELINE.json's: factors
 <= 1e-4 relative Frobenius after one epoch (fp32), losses / metrics <= 1e-3
 absolute, CSR / sampled indices bit-exact, top-k ids exact ties excepted."""
+import os
+
 import numpy as np
 import pytest
 
@@ -285,3 +287,17 @@ def test_tensor_core_row_kernel_epoch(pkg, O, ctx, name, cfg, d):
         assert abs(sg["xi"] - so["xi"]) < 1e-4
     m.close()
     ds.close()
+
+
+def test_multi_gpu_row_sharded_epoch():
+    """2-rank NCCL run of tests/dist_parity.py (skipped on a 1-GPU box)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", os.path.join(helpers.ROOT, "tests", "dist_parity.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "[dist_parity] PASS" in out.stdout
