@@ -301,3 +301,34 @@ def test_multi_gpu_row_sharded_epoch():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "[dist_parity] PASS" in out.stdout
+
+
+@pytest.mark.parametrize("name,flags,epochs", [
+    ("ials", "--uobs_weight 0.1 --l2_reg 0.003", 10),
+    ("safer2", "--uobs_weight 0.004 --l2_reg 0.004 --bandwidth 0.15 --alpha 0.3 --use_snr 0", 10),
+    ("erm_mf", "--uobs_weight 0.004 --l2_reg 0.005", 10),
+    ("safer2pp", "--uobs_weight 0.004 --l2_reg 0.004 --bandwidth 0.15 --block_size 4", 10),
+    ("ialspp", "--uobs_weight 0.1 --l2_reg 0.003 --block_size 4", 10),
+    ("cvar_mf", "--uobs_weight 0.008 --l2_reg 0.002 --stepsize 0.4", 50),
+])
+def test_run_model_cli_reference_thresholds(name, flags, epochs):
+    """The C++ host mirror (include/frecsys + tools/run_model) with the reference's flags on the
+    reference's fixture: the reference's own test assertion NDCG@20 >= 0.2 (tests/*_test.cc:45/99)
+    and the reference's log lines must come out."""
+    import re
+    import subprocess
+    exe = os.path.join(helpers.ROOT, "tools", "run_model")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(helpers.ROOT, "tools")], check=True)
+    cmd = [exe, "--model_name", name, "--dim", "8", "--stdev", "0.1", "--print_train_stats", "1", "--epoch", str(epochs),
+           "--train_data", helpers.fixture_csv("train"), "--test_train_data", helpers.fixture_csv("validation_tr"),
+           "--test_test_data", helpers.fixture_csv("validation_te"), "--init_seed", "1"] + flags.split()
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    log = out.stderr
+    assert len(re.findall(r"Epoch: \d+, Timer: Train=\d+", log)) == epochs
+    assert "Validation Results" in log and "Loss=" in log and "Rec CVaR (q=0.10)@5=" in log
+    ndcg20 = float(re.findall(r"Mean NDCG@5=[\d.]+ Mean NDCG@10=[\d.]+ Mean NDCG@20=([\d.]+)", log)[-1])
+    assert ndcg20 >= 0.2, ndcg20
+    if name in ("safer2", "safer2pp"):
+        assert "Initial Xi:" in log and "Weighted Loss:" in log and "Xi:" in log
