@@ -145,10 +145,11 @@ struct TcLayout {
   static constexpr int kPhaseB = kLstOff + kLstFloats * 4;
   static constexpr int kBigBytes = kStagingBytes > kPhaseB ? kStagingBytes : kPhaseB;
   static constexpr int kRhsOff = kBigBytes;               // rhs partials [2][D]
-  static constexpr int kLdOff = kRhsOff + 2 * D * 4;      // diagonal block scratch [32][33]
-  static constexpr int kWsumOff = kLdOff + 32 * 33 * 4;   // per-warp column sums [P][32]
+  static constexpr int kLdOff = kRhsOff + 2 * D * 4;      // transposed diagonal factor, double-buffered [2][32][32]
+  static constexpr int kWsumOff = kLdOff + 2 * 32 * 32 * 4;  // per-warp column sums [P][32]
   static constexpr int kYOff = kWsumOff + P * 32 * 4;     // y of the current panel [32]
-  static constexpr int kBarOff = ((kYOff + 32 * 4 + 15) / 16) * 16;
+  static constexpr int kRdOff = kYOff + 32 * 4;           // reciprocal diagonal of the current factor, [2][32]
+  static constexpr int kBarOff = ((kRdOff + 2 * 32 * 4 + 15) / 16) * 16;
   static constexpr int kTotal = kBarOff + 64;
   static constexpr int kTmemCols = D == 256 ? 512 : 128;
   __host__ __device__ static constexpr int lst_off(int p) { return 32 * (p * D - 16 * p * (p - 1)); }
@@ -161,7 +162,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
   constexpr int F4 = D / 32;   // float4 loads per loader lane
   constexpr int C = 4 * F4;    // floats per loader lane
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment for the swizzled tiles, by pointer arithmetic on the shared array itself: an
+  // integer round trip makes the compiler lose the address space and emit generic LD/ST for every access.
+  uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* opnd_hi = sm;                      // phase B operand tiles (alias stage 0)
   uint8_t* opnd_lo = sm + L::kTileBytes;
   float* Lst = reinterpret_cast<float*>(sm + L::kLstOff);
@@ -169,6 +172,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
   float* Ld = reinterpret_cast<float*>(sm + L::kLdOff);
   float* wsum = reinterpret_cast<float*>(sm + L::kWsumOff);
   float* yS = reinterpret_cast<float*>(sm + L::kYOff);
+  float* rdiag = reinterpret_cast<float*>(sm + L::kRdOff);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::kBarOff);
   uint64_t* full_bar = bars;       // [2]
   uint64_t* empty_bar = bars + 2;  // [2]
@@ -209,7 +213,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
   uint32_t upd_count = 0;           // trailing-update commits so far (all rows)
   unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long tstamp = clock64();
-#define FRX_DBG_LAP(slot) do { if (p.dbg && tid == 0) { const long long now_ = clock64(); dbg_acc[slot] += (unsigned long long)(now_ - tstamp); tstamp = now_; } } while (0)
+#define FRX_DBG_LAP(slot) do { if (p.dbg && warp == P - 1 && lane == 0) { const long long now_ = clock64(); dbg_acc[slot] += (unsigned long long)(now_ - tstamp); tstamp = now_; } } while (0)
 
   for (int ri = blockIdx.x; ri < p.num_rows; ri += gridDim.x, ++row_count) {
     const int r = p.order[ri];
@@ -413,8 +417,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
         for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(u[j]);
       }
       float* Lp = Lst + L::lst_off(pn);  // panel storage: row (i - c0) -> 32 floats; rows 0..31 hold inv(L11)
+      float* LdT = Ld + (pn & 1) * 1024;  // L11 transposed: LdT[k * 32 + m] = L11[m][k] (double-buffered by panel parity)
+      float* rd = rdiag + (pn & 1) * 32;  // 1 / L11[k][k]
       if (warp == pn) {
-        // -- diagonal block: Cholesky by shuffles (lane = row); 1/l_kk goes to shared memory --
+        // -- diagonal block: right-looking Cholesky by shuffles (lane = row).  The block is symmetric, so the
+        //    pivot row is read from lane k (S[k][j]) and its shuffles do not wait for the rsqrt; the rhs is
+        //    carried along as an extra column so that y = inv(L11) b comes out of the same sweep. --
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
           float akk = __shfl_sync(0xffffffffu, a[k], k);
@@ -423,62 +431,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
             akk = 1.f;
           }
           const float rs = rsqrtf(akk);
-          if (lane == k) wsum[k] = rs;
-          const float lk = a[k] * rs;
+          if (lane == k) rd[k] = rs;
+          const float lk = a[k] * rs;          // L[i][k] of this lane's row (lane k: sqrt(pivot))
+          const float t = lk * rs;             // S[i][k] / pivot
           a[k] = lk;
+          const float yk = __shfl_sync(0xffffffffu, b_reg, k) * rs;  // y_k = b_k / L_kk
+          if (lane == k) b_reg = yk;
+          else if (lane > k) b_reg = fmaf(-lk, yk, b_reg);
 #pragma unroll
           for (int j = k + 1; j < 32; ++j) {
-            const float lj = __shfl_sync(0xffffffffu, lk, j);
-            a[j] = fmaf(-lk, lj, a[j]);
+            const float skj = __shfl_sync(0xffffffffu, a[j], k);  // S[k][j] = S[j][k]
+            a[j] = fmaf(-t, skj, a[j]);
           }
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          if (j > lane) a[j] = 0.f;     // strict upper part of the block
-          Ld[lane * 33 + j] = a[j];
+          if (j > lane) a[j] = 0.f;     // strict upper part of the factor
+          LdT[j * 32 + lane] = a[j];
         }
-        __syncwarp();
-        // -- inverse of L11 by columns: lane c solves L x = e_c (column sweep) --
-        float x[32];
-#pragma unroll
-        for (int i2 = 0; i2 < 32; ++i2) x[i2] = (i2 == lane) ? 1.f : 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          x[j] *= wsum[j];
-#pragma unroll
-          for (int i2 = j + 1; i2 < 32; ++i2) x[i2] = fmaf(-Ld[i2 * 33 + j], x[j], x[i2]);
-        }
-        // lane c holds column c of inv(L11): store as Lp[i][c]; y = inv(L11) * b via a transpose-reduce
-#pragma unroll
-        for (int i2 = 0; i2 < 32; ++i2) {
-          Lp[i2 * 32 + ((((lane >> 2) ^ (i2 & 7)) & 7) << 2) + (lane & 3)] = x[i2];
-          x[i2] *= b_reg;
-        }
-        transpose_reduce<32>(x, lane);
-        b_reg = x[0];  // y_i of this row
-        yS[lane] = b_reg;
+        yS[lane] = b_reg;               // y_i of this row
       }
-      __syncthreads();  // inv(L11) and y of the panel are visible
-      FRX_DBG_LAP(3);  // panel load + diagonal block factor / inverse
-      long long w7t = 0;
-      if (p.dbg && warp == P - 1 && lane == 0) w7t = clock64();
+      __syncthreads();  // L11, 1/diag and y of the panel are visible
+      FRX_DBG_LAP(3);  // panel load + diagonal block factor (barrier wait lands in the next lap: BAR is deferred-blocking)
       if (is_row_warp && warp > pn) {
-        // -- rows below: L21 row = a * inv(L11)^T (in place, descending k), then forward substitution --
+        // -- rows below: L21 row by forward substitution against L11 (column sweep, in place) --
 #pragma unroll
-        for (int k = 31; k >= 0; --k) {
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-          const float4* lrow = reinterpret_cast<const float4*>(Lp + k * 32);
+        for (int k = 0; k < 32; ++k) {
+          const float l = a[k] * rd[k];
+          a[k] = l;
+          const float4* col = reinterpret_cast<const float4*>(LdT + k * 32);
 #pragma unroll
-          for (int j4 = 0; j4 <= k / 4; ++j4) {
-            const float4 l4 = lrow[(j4 ^ (k & 7)) & 7];
-            s0 = fmaf(a[4 * j4], l4.x, s0);
-            if (4 * j4 + 1 <= k) s1 = fmaf(a[4 * j4 + 1], l4.y, s1);
-            if (4 * j4 + 2 <= k) s2 = fmaf(a[4 * j4 + 2], l4.z, s2);
-            if (4 * j4 + 3 <= k) s3 = fmaf(a[4 * j4 + 3], l4.w, s3);
+          for (int m4 = (k + 1) / 4; m4 < 8; ++m4) {
+            const float4 c = col[m4];
+            if (4 * m4 + 0 > k) a[4 * m4 + 0] = fmaf(-l, c.x, a[4 * m4 + 0]);
+            if (4 * m4 + 1 > k) a[4 * m4 + 1] = fmaf(-l, c.y, a[4 * m4 + 1]);
+            if (4 * m4 + 2 > k) a[4 * m4 + 2] = fmaf(-l, c.z, a[4 * m4 + 2]);
+            if (4 * m4 + 3 > k) a[4 * m4 + 3] = fmaf(-l, c.w, a[4 * m4 + 3]);
           }
-          const float s = (s0 + s1) + (s2 + s3);
-          a[k] = s;
         }
+        const int i = 32 * warp + lane;
+        float4* dst = reinterpret_cast<float4*>(Lp + (size_t)(i - c0) * 32);
         float dot = 0.f;
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
@@ -487,16 +479,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
           dot = fmaf(a[4 * k4 + 1], y4.y, dot);
           dot = fmaf(a[4 * k4 + 2], y4.z, dot);
           dot = fmaf(a[4 * k4 + 3], y4.w, dot);
+          dst[(k4 ^ (lane & 7)) & 7] = make_float4(a[4 * k4], a[4 * k4 + 1], a[4 * k4 + 2], a[4 * k4 + 3]);
         }
-        b_reg -= dot;
-        if (p.dbg && warp == P - 1 && lane == 0) { const long long n_ = clock64(); atomicAdd(p.dbg + 8, (unsigned long long)(n_ - w7t)); w7t = n_; }
-        const int i = 32 * warp + lane;
-        float4* dst = reinterpret_cast<float4*>(Lp + (size_t)(i - c0) * 32);
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4)
-          dst[(c4 ^ (lane & 7)) & 7] = make_float4(a[4 * c4], a[4 * c4 + 1], a[4 * c4 + 2], a[4 * c4 + 3]);
-        if (p.dbg && warp == P - 1 && lane == 0) { const long long n_ = clock64(); atomicAdd(p.dbg + 9, (unsigned long long)(n_ - w7t)); w7t = n_; }
+        b_reg -= dot;  // forward substitution: b_i -= L21[i][:] . y_p
       }
+      FRX_DBG_LAP(6);  // wait for the diagonal warp + triangular solve (this warp)
       if (c1 < D) {
         if (is_row_warp && warp >= pn) {
           // -- L panel rows as K-major tf32 hi/lo operand tiles --
@@ -515,11 +502,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
             *reinterpret_cast<float4*>(opnd_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
           }
         }
-        if (p.dbg && warp == P - 1 && lane == 0) { const long long n_ = clock64(); atomicAdd(p.dbg + 10, (unsigned long long)(n_ - w7t)); w7t = n_; }
+        FRX_DBG_LAP(7);  // operand tiles (this warp)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
         __syncthreads();
-        if (p.dbg && warp == P - 1 && lane == 0) { const long long n_ = clock64(); atomicAdd(p.dbg + 11, (unsigned long long)(n_ - w7t)); w7t = n_; }
         FRX_DBG_LAP(4);  // TRSM + operand tiles
         if (warp == TC_LOADER_WARPS) {
           tc_fence_after();
@@ -552,6 +538,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
           __syncwarp();
         }
         ++upd_count;
+      }
+      if (warp == pn) {
+        // -- off the critical path (the tensor cores are busy with the trailing update, the other warps wait for
+        //    it): inv(L11) by columns, lane c solves L x = e_c with a column sweep; kept for the back substitution --
+        float x[32];
+#pragma unroll
+        for (int i2 = 0; i2 < 32; ++i2) x[i2] = (i2 == lane) ? 1.f : 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          x[j] *= rd[j];
+          const float4* col = reinterpret_cast<const float4*>(LdT + j * 32);
+#pragma unroll
+          for (int m4 = (j + 1) / 4; m4 < 8; ++m4) {
+            const float4 c = col[m4];
+            if (4 * m4 + 0 > j) x[4 * m4 + 0] = fmaf(-c.x, x[j], x[4 * m4 + 0]);
+            if (4 * m4 + 1 > j) x[4 * m4 + 1] = fmaf(-c.y, x[j], x[4 * m4 + 1]);
+            if (4 * m4 + 2 > j) x[4 * m4 + 2] = fmaf(-c.z, x[j], x[4 * m4 + 2]);
+            if (4 * m4 + 3 > j) x[4 * m4 + 3] = fmaf(-c.w, x[j], x[4 * m4 + 3]);
+          }
+        }
+#pragma unroll
+        for (int i2 = 0; i2 < 32; ++i2)
+          Lp[i2 * 32 + ((((lane >> 2) ^ (i2 & 7)) & 7) << 2) + (lane & 3)] = x[i2];  // lane c holds column c
       }
     }
     __syncthreads();
@@ -603,10 +612,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
     FRX_DBG_LAP(5);  // back substitution + store
   }
 
-  if (p.dbg && tid == 0) {
-    for (int i = 0; i < 6; ++i) atomicAdd(p.dbg + i, dbg_acc[i]);
-    atomicAdd(p.dbg + 6, (unsigned long long)row_count);
+  if (p.dbg && warp == P - 1 && lane == 0) {
+    for (int i = 0; i < 8; ++i) atomicAdd(p.dbg + i + (i >= 6 ? 2 : 0), dbg_acc[i]);
   }
+  if (p.dbg && tid == 0) atomicAdd(p.dbg + 6, (unsigned long long)row_count);
   tc_fence_before();
   __syncthreads();
   if (warp == TC_LOADER_WARPS)
