@@ -430,10 +430,19 @@ static int gramian_into(frx_model* m, const float* E, int n, int cs, int bd, int
     b = (int)((long long)n * c->rank / c->world);
     e = (int)((long long)n * (c->rank + 1) / c->world);
   }
-  int rc = c->ensure_gram_ws(gramian_workspace_floats(e - b, bd, fd, c->num_sms));
-  if (rc) return rc;
-  launch_gramian(E + (size_t)b * d, e - b, d, cs, bd, fs, fd, w ? w + b : nullptr, out + (size_t)cs * d + fs, d,
-                 c->gram_ws, c->gram_ws_floats, c->stream, c->num_sms, &c->launches);
+  static const bool disable_tc = getenv("FRX_DISABLE_TC") != nullptr;
+  if (!disable_tc && gramian_tc_supported(e - b, d, cs, bd, fs, fd)) {
+    int rc = c->ensure_gram_ws(gramian_tc_workspace_floats(d, c->num_sms));
+    if (rc) return rc;
+    if (launch_gramian_tc(E + (size_t)b * d, e - b, d, w ? w + b : nullptr, out, c->gram_ws, c->stream, c->num_sms,
+                          &c->launches) != 0)
+      return fail(FRX_ERR_CUDA, "cuTensorMapEncodeTiled failed for the Gramian operand");
+  } else {
+    int rc = c->ensure_gram_ws(gramian_workspace_floats(e - b, bd, fd, c->num_sms));
+    if (rc) return rc;
+    launch_gramian(E + (size_t)b * d, e - b, d, cs, bd, fs, fd, w ? w + b : nullptr, out + (size_t)cs * d + fs, d,
+                   c->gram_ws, c->gram_ws_floats, c->stream, c->num_sms, &c->launches);
+  }
   CK(cudaGetLastError());
   if (c->world > 1) {
     if (fs != 0 || fd != d) return fail(FRX_ERR_ARG, "sharded Gramian needs full-width strips");
@@ -1145,9 +1154,17 @@ extern "C" int frx_gramian(frx_context* c, const float* E, int n, int d, const f
     CK(cudaMalloc(&dw, sizeof(float) * (size_t)n));
     CK(cudaMemcpyAsync(dw, w, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
   }
-  int rc = c->ensure_gram_ws(gramian_workspace_floats(n, d, d, c->num_sms));
-  if (rc) return rc;
-  launch_gramian(dE, n, d, 0, d, 0, d, dw, dG, d, c->gram_ws, c->gram_ws_floats, c->stream, c->num_sms, &c->launches);
+  static const bool disable_tc = getenv("FRX_DISABLE_TC") != nullptr;
+  if (!disable_tc && gramian_tc_supported(n, d, 0, d, 0, d)) {
+    int rc = c->ensure_gram_ws(gramian_tc_workspace_floats(d, c->num_sms));
+    if (rc) return rc;
+    if (launch_gramian_tc(dE, n, d, dw, dG, c->gram_ws, c->stream, c->num_sms, &c->launches) != 0)
+      return fail(FRX_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  } else {
+    int rc = c->ensure_gram_ws(gramian_workspace_floats(n, d, d, c->num_sms));
+    if (rc) return rc;
+    launch_gramian(dE, n, d, 0, d, 0, d, dw, dG, d, c->gram_ws, c->gram_ws_floats, c->stream, c->num_sms, &c->launches);
+  }
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, dG, sizeof(float) * (size_t)d * d, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));

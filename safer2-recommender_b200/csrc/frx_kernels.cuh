@@ -65,6 +65,12 @@ void launch_gramian(const float* E, int n, int d, int cs, int bd, int fs, int fd
                     cudaStream_t s, int num_sms, long long* launches);
 size_t gramian_workspace_floats(int n, int bd, int fd, int num_sms);
 
+// tcgen05 + TMA Gramian (frx_gramian_tc.cu): full d x d, d = 128 or 256.  Returns 0 on success.
+bool gramian_tc_supported(int n, int d, int cs, int bd, int fs, int fd);
+size_t gramian_tc_workspace_floats(int d, int num_sms);
+int launch_gramian_tc(const float* E, int n, int d, const float* w, float* out, float* workspace, cudaStream_t s,
+                      int num_sms, long long* launches);
+
 struct LossParams {
   const int* ptr;
   const int* col;
