@@ -72,6 +72,9 @@ void* frx_context_stream(frx_context* ctx);
  * rank 0 calls frx_comm_unique_id and ships the 128 bytes to every rank. */
 int frx_comm_unique_id(void* out128);
 int frx_context_init_comm(frx_context* ctx, int rank, int world_size, const void* unique_id128);
+/* Host-only: the contiguous row ranges the ranks own, balanced on sum(history length + row_unit);
+ * ptr[nrows+1] is a CSR row pointer, rank_begin receives world+1 entries. */
+int frx_partition_rows(const int* ptr, int nrows, int world, int row_unit, int* rank_begin);
 
 /* ---- dataset: replaces frecsys::Dataset's by_user_/by_item_ build ---------
  * (include/frecsys/dataset.h:71-99).  Input is the tuple list in FILE order;

@@ -442,6 +442,12 @@ class Model {
   std::vector<std::vector<int>> last_snr_indices;  // what ComputeXi drew last
   bool print_train_stats = false;
   LossStats last_stats;
+  // Test hooks for emulating the row-sharded multi-GPU epoch on the CPU (tests/test_dist_cpu.py): only rows
+  // in [row_lo, row_hi) are solved, and StepV can be handed an externally reduced weighted Gramian.
+  int row_lo = 0, row_hi = std::numeric_limits<int>::max();
+  bool use_gz_override = false;
+  Mat gz_override;
+  bool InRange(int r) const { return r >= row_lo && r < row_hi; }
 
   Model(const Config& c, int nu, int ni, unsigned init_seed)
       : cfg(c), num_users(nu), num_items(ni), U(nu, c.dim), V(ni, c.dim) {
@@ -513,7 +519,7 @@ class Model {
     const bool halve = !is_ials_family();
     ParallelFor((int)data.by_user.size(), [&](int u) {
       const SpVector& h = data.by_user[u];
-      if (h.empty()) return;
+      if (h.empty() || !InRange(u)) return;
       user_loss[u] = ComputeLoss(h, U.row(u), V, G, cfg.uobs_weight, halve, pred);
     });
   }
@@ -661,7 +667,7 @@ class Model {
     const int num_other = other.rows;
     ParallelFor((int)rows.size(), [&](int r) {
       const SpVector& h = rows[r];
-      if (h.empty()) return;
+      if (h.empty() || !InRange(r)) return;
       float reg = IalsReg((int)h.size(), num_other);
       ProjectIals(h, other, G, reg, out->row(row_map ? (*row_map)[r] : r));
     });
@@ -674,7 +680,7 @@ class Model {
     const int num_items_ = items.rows;
     ParallelFor((int)rows.size(), [&](int u) {
       const SpVector& h = rows[u];
-      if (h.empty()) return;
+      if (h.empty() || !InRange(u)) return;
       float weight = weight_of ? weight_of[u] : 1.0f;
       float reg = UserReg(num_items_);
       ProjectU(h, items, G, reg, weight, out->row(row_map ? (*row_map)[u] : u));
@@ -685,11 +691,11 @@ class Model {
   void StepV(const Dataset& data, const Mat& users, Mat* items) const {
     std::vector<float> norm_dual_weight(num_users);  // z / |hist| (inf/NaN for empty: never read)
     for (int u = 0; u < num_users; ++u) norm_dual_weight[u] = dual_weight[u] / user_history_size[u];
-    Mat G = Gramian(users, dual_weight.data());      // U^T diag(z) U over ALL rows, safer2.h:504-509
+    Mat G = use_gz_override ? gz_override : Gramian(users, dual_weight.data());  // U^T diag(z) U over ALL rows, safer2.h:504-509
     const int nu = users.rows;
     ParallelFor((int)data.by_item.size(), [&](int v) {
       const SpVector& h = data.by_item[v];
-      if (h.empty()) return;
+      if (h.empty() || !InRange(v)) return;
       float reg = ItemReg(v, nu);
       ProjectV(h, users, G, reg, norm_dual_weight.data(), items->row(v));
     });

@@ -61,7 +61,14 @@ def build(force=False):
     """Compile the oracle with the reference's flags (-O3 -march=native).  The
     .so is rebuilt when the host CPU differs from the one it was built on, so a
     library built in the dev container is never run with foreign -march code."""
+    import fcntl
     sig = _cpu_sig()
+    with open(os.path.join(HERE, ".oracle_build_lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)  # several ranks / test workers may get here at once
+        return _build_locked(sig, force)
+
+
+def _build_locked(sig, force):
     srcs = [os.path.join(HERE, f) for f in ("oracle_capi.cc", "oracle_rng.cc", "frecsys_oracle.hpp", "Makefile")]
     newest = max(os.path.getmtime(s) for s in srcs)
     ok = (os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == sig
@@ -112,6 +119,10 @@ def lib():
         L.orc_gramian.argtypes = [fp, C.c_int, C.c_int, fp, fp]
         L.orc_init_factors.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_uint, fp, fp]
         L.orc_num_threads.restype = C.c_int
+        L.orc_model_set_range.argtypes = [vp, C.c_int, C.c_int]
+        L.orc_model_put_factors.argtypes = [vp, fp, fp]
+        L.orc_model_set_item_gramian.argtypes = [vp, fp]
+        L.orc_model_set_gz_override.argtypes = [vp, fp]
         _lib = L
     return _lib
 
@@ -186,6 +197,23 @@ class Model:
 
     def initialize(self, ds):
         lib().orc_model_initialize(self.h, ds.h)
+
+    # hooks for the CPU emulation of the row-sharded epoch
+    def set_range(self, lo, hi):
+        lib().orc_model_set_range(self.h, int(lo), int(hi))
+
+    def put_factors(self, U=None, V=None):
+        U = None if U is None else np.ascontiguousarray(U, np.float32)
+        V = None if V is None else np.ascontiguousarray(V, np.float32)
+        lib().orc_model_put_factors(self.h, _fp(U), _fp(V))
+
+    def set_item_gramian(self, G):
+        G = np.ascontiguousarray(G, np.float32)
+        lib().orc_model_set_item_gramian(self.h, _fp(G))
+
+    def set_gz_override(self, G):
+        G = None if G is None else np.ascontiguousarray(G, np.float32)
+        lib().orc_model_set_gz_override(self.h, _fp(G))
 
     def train(self, ds):
         lib().orc_model_train(self.h, ds.h)

@@ -182,4 +182,24 @@ void orc_init_factors(int nu, int ni, int d, float stdev, unsigned seed, float* 
 
 int orc_num_threads() { return NumThreads(); }
 
+// ---- hooks for the CPU emulation of the row-sharded epoch (tests/test_dist_cpu.py) ----
+void orc_model_set_range(void* mv, int lo, int hi) { ((Model*)mv)->row_lo = lo; ((Model*)mv)->row_hi = hi; }
+void orc_model_put_factors(void* mv, const float* U, const float* V) {  // overwrite without resetting the state
+  Model* m = (Model*)mv;
+  if (U) std::copy(U, U + m->U.a.size(), m->U.a.begin());
+  if (V) std::copy(V, V + m->V.a.size(), m->V.a.begin());
+}
+void orc_model_set_item_gramian(void* mv, const float* G) {
+  Model* m = (Model*)mv;
+  std::copy(G, G + m->item_gramian.a.size(), m->item_gramian.a.begin());
+}
+void orc_model_set_gz_override(void* mv, const float* G) {
+  Model* m = (Model*)mv;
+  m->use_gz_override = G != nullptr;
+  if (G) {
+    m->gz_override = Mat(m->cfg.dim, m->cfg.dim);
+    std::copy(G, G + m->gz_override.a.size(), m->gz_override.a.begin());
+  }
+}
+
 }  // extern "C"

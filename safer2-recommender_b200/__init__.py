@@ -19,7 +19,7 @@ MODEL_IDS = {"ials": 0, "ialspp": 1, "erm_mf": 2, "cvar_mf": 3, "safer2": 4, "sa
 
 EXPORTS = [
     "frx_last_error", "frx_context_create", "frx_context_destroy", "frx_context_sync",
-    "frx_context_stream", "frx_comm_unique_id", "frx_context_init_comm", "frx_dataset_create",
+    "frx_context_stream", "frx_comm_unique_id", "frx_context_init_comm", "frx_partition_rows", "frx_dataset_create",
     "frx_dataset_destroy", "frx_dataset_info", "frx_dataset_get_csr", "frx_model_create",
     "frx_model_destroy", "frx_model_init_factors", "frx_model_set_factors", "frx_model_get_factors", "frx_model_upload_factors",
     "frx_model_initialize", "frx_model_train", "frx_model_stage", "frx_model_get_state",
@@ -91,6 +91,7 @@ def lib():
     L.frx_context_stream.restype = vp
     L.frx_comm_unique_id.argtypes = [vp]
     L.frx_context_init_comm.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.frx_partition_rows.argtypes = [ip, C.c_int, C.c_int, C.c_int, ip]
     L.frx_dataset_create.argtypes = [vp, C.c_int, ip, ip, C.POINTER(vp)]
     L.frx_dataset_destroy.argtypes = [vp]
     L.frx_dataset_destroy.restype = None
@@ -179,6 +180,14 @@ class Context:
         if self.h:
             lib().frx_context_destroy(self.h)
             self.h = None
+
+
+def partition_rows(ptr, world, row_unit=256):
+    """Row ranges per rank for the row-sharded epoch (host-only; mirrors what frx_dataset_create uses)."""
+    ptr = np.ascontiguousarray(ptr, np.int32)
+    out = np.zeros(world + 1, np.int32)
+    _check(lib().frx_partition_rows(_ip(ptr), len(ptr) - 1, world, row_unit, _ip(out)))
+    return out
 
 
 def read_csv_tuples(path):

@@ -255,23 +255,32 @@ extern "C" int frx_context_init_comm(frx_context* c, int rank, int world, const 
 // ---------------------------------------------------------------------------
 // dataset
 // ---------------------------------------------------------------------------
+// Cost model of one row for the multi-GPU partition: history length + a fixed per-row share for the
+// d x d factorisation, in units of history entries.
+static const int kRowUnit = 256;
+
+// Contiguous row ranges balanced on sum(history length + row_unit).  Pure host code (no GPU needed).
+extern "C" int frx_partition_rows(const int* ptr, int nrows, int world, int row_unit, int* rank_begin) {
+  if (!ptr || !rank_begin || nrows < 0 || world < 1 || row_unit < 0) return fail(FRX_ERR_ARG, "bad partition arguments");
+  for (int k = 0; k <= world; ++k) rank_begin[k] = nrows;
+  rank_begin[0] = 0;
+  const long long total = (long long)(ptr[nrows] - ptr[0]) + (long long)nrows * row_unit;
+  int k = 1;
+  for (int r = 0; r < nrows && k < world; ++r) {
+    const long long done = (long long)(ptr[r + 1] - ptr[0]) + (long long)(r + 1) * row_unit;
+    while (k < world && done * world >= total * k) rank_begin[k++] = r + 1;
+  }
+  return FRX_OK;
+}
+
 static int finish_csr(frx_context* c, Csr& m, const int* cost_other_dim) {
   (void)cost_other_dim;
   m.h_ptr.resize(m.nrows + 1);
   CK(cudaMemcpyAsync(m.h_ptr.data(), m.ptr, sizeof(int) * (m.nrows + 1), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  // Row-id ranges per rank, balanced on history length; rank k owns [rank_begin[k], rank_begin[k+1]).
+  // Row-id ranges per rank; rank k owns [rank_begin[k], rank_begin[k+1]).
   m.rank_begin.assign(c->world + 1, m.nrows);
-  m.rank_begin[0] = 0;
-  {
-    const long long total = m.h_ptr[m.nrows] + (long long)m.nrows;  // nnz + one unit per row
-    int k = 1;
-    for (int r = 0; r < m.nrows && k < c->world; ++r) {
-      const long long done = m.h_ptr[r + 1] + (long long)(r + 1);
-      while (k < c->world && done >= total * k / c->world) m.rank_begin[k++] = r + 1;
-    }
-    for (; k < c->world; ++k) m.rank_begin[k] = m.nrows;
-  }
+  frx_partition_rows(m.h_ptr.data(), m.nrows, c->world, kRowUnit, m.rank_begin.data());
   std::vector<int> order;
   m.distinct = 0;
   for (int r = 0; r < m.nrows; ++r)

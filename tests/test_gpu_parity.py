@@ -332,3 +332,26 @@ def test_run_model_cli_reference_thresholds(name, flags, epochs):
     assert ndcg20 >= 0.2, ndcg20
     if name in ("safer2", "safer2pp"):
         assert "Initial Xi:" in log and "Weighted Loss:" in log and "Xi:" in log
+
+
+@pytest.mark.parametrize("d", [64, 512])
+@pytest.mark.parametrize("name,cfg", [
+    ("ials", dict(uobs_weight=0.1, reg=0.003)),
+    ("safer2", dict(uobs_weight=0.004, reg=0.004, bandwidth=0.15)),
+])
+def test_generic_row_kernel_large_dims(pkg, O, ctx, name, cfg, d):
+    """d = 64 keeps the system in shared memory; d = 512 (the MSD configs) does not fit and runs the
+    generic kernel with the per-CTA system in global scratch."""
+    nu, ni = 120, 150
+    users, items = helpers.synth_tuples(nu, ni, 20, seed=44, heavy_rows=[(0, 1), (4, 129), (5, 140)], empty_users=(7,))
+    ods, om, ds, m = make_pair(pkg, O, ctx, users, items, nu, ni, model=name, dim=d, **cfg)
+    om.initialize(ods)
+    m.initialize(ds)
+    om.train(ods)
+    m.train(ds)
+    U, V = m.factors()
+    Uo, Vo = om.factors()
+    assert rel_fro(U, Uo) < FACTOR_TOL, rel_fro(U, Uo)
+    assert rel_fro(V, Vo) < FACTOR_TOL, rel_fro(V, Vo)
+    m.close()
+    ds.close()
