@@ -355,3 +355,48 @@ def test_generic_row_kernel_large_dims(pkg, O, ctx, name, cfg, d):
     assert rel_fro(V, Vo) < FACTOR_TOL, rel_fro(V, Vo)
     m.close()
     ds.close()
+
+
+def _ref_cases():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_ref_golden", os.path.join(helpers.GOLDEN, "make_ref_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.CASES
+
+
+@pytest.mark.parametrize("case", sorted(c for c in _ref_cases() if "cg" not in c))
+def test_cuda_matches_reference_goldens(pkg, ctx, case):
+    """The CUDA path against the golden vectors produced by the reference's own headers (oracle/_ref,
+    tests/golden/make_ref_golden.py) on the reference's fixture: the north-star bar — factors after one
+    epoch <= 1e-4 relative Frobenius; xi / weighted state / Recall@k / NDCG@k within 1e-3."""
+    model, dim, epochs, flags = _ref_cases()[case]
+    g = np.load(os.path.join(helpers.GOLDEN, "ref_golden.npz"))
+    tr = pkg.Dataset.from_csv(ctx, helpers.fixture_csv("train"))
+    vtr = pkg.Dataset.from_csv(ctx, helpers.fixture_csv("validation_tr"))
+    vte = pkg.Dataset.from_csv(ctx, helpers.fixture_csv("validation_te"))
+    m = pkg.Model(ctx, tr.max_user + 1, tr.max_item + 1, model=model, dim=dim, **flags)
+    m.init_factors(1)
+    m.initialize(tr)
+    mws = []
+    for _ in range(epochs):
+        m.train(tr)
+        mws.append(m.scalars()["mean_weight"])
+    U, V = m.factors()
+    st = m.state()
+    tol = FACTOR_TOL if epochs == 1 else 5 * FACTOR_TOL
+    assert rel_fro(U[::8], g[case + "/U"]) < tol, rel_fro(U[::8], g[case + "/U"])
+    assert rel_fro(V[::8], g[case + "/V"]) < tol, rel_fro(V[::8], g[case + "/V"])
+    assert abs(st["xi"] - float(g[case + "/xi"][0])) < 1e-3
+    if len(g[case + "/z"]):
+        np.testing.assert_allclose(st["z"][::8], g[case + "/z"], atol=1e-3)
+    if len(g[case + "/loss"]):
+        np.testing.assert_allclose(st["loss"][::8], g[case + "/loss"], rtol=1e-3, atol=1e-5)
+    if len(g[case + "/mean_weights"]):
+        np.testing.assert_allclose(mws, g[case + "/mean_weights"], atol=1e-3)
+    ev = m.evaluate(vtr, vte)
+    np.testing.assert_allclose(ev["recall"].mean(0), g[case + "/recall"], atol=1e-3)
+    np.testing.assert_allclose(ev["ndcg"].mean(0), g[case + "/ndcg"], atol=1e-3)
+    for t in (tr, vtr, vte):
+        t.close()
+    m.close()
