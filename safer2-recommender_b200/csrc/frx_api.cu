@@ -627,8 +627,8 @@ static int run_rows(frx_model* m, const RowCall& rc_) {
       const double rows = h[6] ? (double)h[6] : 1.0;
       fprintf(stderr, "[frx tc] mode=%d rows=%llu cycles/row: gather+syrk=%.0f assemble=%.0f upd_wait=%.0f diag=%.0f trsm+tiles=%.0f backsub=%.0f\n",
               p.mode, h[6], h[0] / rows, h[1] / rows, h[2] / rows, h[3] / rows, h[4] / rows, h[5] / rows);
-      fprintf(stderr, "[frx tc]   (timeline of the last row-warp) trsm=%.0f opnd_tiles=%.0f; trsm+tiles above = fence+barrier only\n",
-              h[8] / rows, h[9] / rows);
+      fprintf(stderr, "[frx tc]   (timeline of the last row-warp) wait_diag+trsm=%.0f opnd_tiles=%.0f | diag warps: factor=%.0f | last row-warp pure trsm=%.0f\n",
+              h[8] / rows, h[9] / rows, h[10] / rows, h[11] / rows);
     }
     return FRX_OK;
   }

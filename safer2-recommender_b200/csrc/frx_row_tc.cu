@@ -423,17 +423,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
         // -- diagonal block: right-looking Cholesky by shuffles (lane = row).  The block is symmetric, so the
         //    pivot row is read from lane k (S[k][j]) and its shuffles do not wait for the rsqrt; the rhs is
         //    carried along as an extra column so that y = inv(L11) b comes out of the same sweep. --
+        long long dgt0 = 0;
+        if (p.dbg && lane == 0) dgt0 = clock64();
+        // Right-looking Cholesky by shuffles, lane = row.  The block is symmetric, so the pivot row is read
+        // from lane k (S[k][j]) and the next pivot comes from the lane's OWN column-k entry
+        // (S[k+1][k] = S[k][k+1]): its shuffle + rsqrt are issued before the bulk rank-1 update of step k.
+        // (Measured alternatives: publishing the pivot row through shared memory is slower; a single warp
+        // sustains ~4 cycles per instruction here, the 256 sequential pivots of a row are the latency floor.)
+        float rs;
+        {
+          float akk = __shfl_sync(0xffffffffu, a[0], 0);
+          if (!(akk > 0.f)) { if (lane == 0) atomicExch(p.status, 1); akk = 1.f; }
+          rs = rsqrtf(akk);
+        }
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
-          float akk = __shfl_sync(0xffffffffu, a[k], k);
-          if (!(akk > 0.f)) {
-            if (lane == 0) atomicExch(p.status, 1);
-            akk = 1.f;
-          }
-          const float rs = rsqrtf(akk);
-          if (lane == k) rd[k] = rs;
           const float lk = a[k] * rs;          // L[i][k] of this lane's row (lane k: sqrt(pivot))
           const float t = lk * rs;             // S[i][k] / pivot
+          float rs_next = 0.f;
+          if (k + 1 < 32) {
+            const float dcand = fmaf(-t, a[k], a[k + 1]);  // valid in lane k+1: next pivot
+            float akk = __shfl_sync(0xffffffffu, dcand, k + 1);
+            if (!(akk > 0.f)) { if (lane == 0) atomicExch(p.status, 1); akk = 1.f; }
+            rs_next = rsqrtf(akk);
+          }
+          if (lane == k) rd[k] = rs;
           a[k] = lk;
           const float yk = __shfl_sync(0xffffffffu, b_reg, k) * rs;  // y_k = b_k / L_kk
           if (lane == k) b_reg = yk;
@@ -443,6 +457,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
             const float skj = __shfl_sync(0xffffffffu, a[j], k);  // S[k][j] = S[j][k]
             a[j] = fmaf(-t, skj, a[j]);
           }
+          rs = rs_next;
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -450,11 +465,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
           LdT[j * 32 + lane] = a[j];
         }
         yS[lane] = b_reg;               // y_i of this row
+        if (p.dbg && lane == 0) atomicAdd(p.dbg + 10, (unsigned long long)(clock64() - dgt0));
       }
       __syncthreads();  // L11, 1/diag and y of the panel are visible
       FRX_DBG_LAP(3);  // panel load + diagonal block factor (barrier wait lands in the next lap: BAR is deferred-blocking)
       if (is_row_warp && warp > pn) {
         // -- rows below: L21 row by forward substitution against L11 (column sweep, in place) --
+        long long trt0 = 0;
+        if (p.dbg && warp == P - 1 && lane == 0) { volatile float probe = rd[0]; (void)probe; trt0 = clock64(); }
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
           const float l = a[k] * rd[k];
@@ -482,6 +500,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
           dst[(k4 ^ (lane & 7)) & 7] = make_float4(a[4 * k4], a[4 * k4 + 1], a[4 * k4 + 2], a[4 * k4 + 3]);
         }
         b_reg -= dot;  // forward substitution: b_i -= L21[i][:] . y_p
+        if (p.dbg && warp == P - 1 && lane == 0) atomicAdd(p.dbg + 11, (unsigned long long)(clock64() - trt0));
       }
       FRX_DBG_LAP(6);  // wait for the diagonal warp + triangular solve (this warp)
       if (c1 < D) {
