@@ -242,6 +242,35 @@ __global__ void __launch_bounds__(256) user_loss_kernel(LossParams p) {
       for (int k = lane; k < d; k += 32) us[k] = p.U[(size_t)u * d + k];
       __syncwarp();
       int e = 0;
+      if ((d & 127) == 0) {
+        // vector path: each lane owns float4 slices (coalesced 512 B per warp load), 8 history entries in flight
+        for (; e + 8 <= n; e += 8) {
+          const float* vp[8];
+          float acc[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            vp[q] = p.V + (size_t)__ldg(p.col + beg + e + q) * d;
+            acc[q] = 0.f;
+          }
+          for (int k = lane * 4; k < d; k += 128) {
+            const float4 u4 = *reinterpret_cast<const float4*>(us + k);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 v4 = __ldg(reinterpret_cast<const float4*>(vp[q] + k));
+              acc[q] = fmaf(v4.x, u4.x, acc[q]);
+              acc[q] = fmaf(v4.y, u4.y, acc[q]);
+              acc[q] = fmaf(v4.z, u4.z, acc[q]);
+              acc[q] = fmaf(v4.w, u4.w, acc[q]);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const double sq = (double)(warp_sum(acc[q]) - 1.f);
+            loss = (float)((double)loss + sq * sq);
+            obs += sq * sq;
+          }
+        }
+      }
       for (; e + 4 <= n; e += 4) {
         const float* v0 = p.V + (size_t)p.col[beg + e] * d;
         const float* v1 = p.V + (size_t)p.col[beg + e + 1] * d;
