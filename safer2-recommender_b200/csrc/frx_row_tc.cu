@@ -36,6 +36,13 @@ constexpr int KT = 32;                                  // entries per operand t
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// MUFU.RSQ without the denormal fix-up of rsqrtf(); the pivots are normal numbers >= reg.
+__device__ __forceinline__ float fast_rsqrt(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -431,40 +438,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
         // (Measured alternatives: publishing the pivot row through shared memory is slower; a single warp
         // sustains ~4 cycles per instruction here, the 256 sequential pivots of a row are the latency floor.)
         float rs;
+        bool bad_pivot;  // warp-uniform; reported once after the sweep so that the loop stays branch-free
         {
           float akk = __shfl_sync(0xffffffffu, a[0], 0);
-          if (!(akk > 0.f)) { if (lane == 0) atomicExch(p.status, 1); akk = 1.f; }
-          rs = rsqrtf(akk);
+          bad_pivot = !(akk > 0.f);
+          rs = fast_rsqrt(bad_pivot ? 1.f : akk);
         }
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
           const float lk = a[k] * rs;          // L[i][k] of this lane's row (lane k: sqrt(pivot))
-          const float t = lk * rs;             // S[i][k] / pivot
+          // column k of the factor goes to shared memory with ONE store (it is the transposed factor the
+          // rows below need anyway); every lane then reads it back as broadcast float4s
+          LdT[k * 32 + lane] = lane >= k ? lk : 0.f;
           float rs_next = 0.f;
           if (k + 1 < 32) {
-            const float dcand = fmaf(-t, a[k], a[k + 1]);  // valid in lane k+1: next pivot
-            float akk = __shfl_sync(0xffffffffu, dcand, k + 1);
-            if (!(akk > 0.f)) { if (lane == 0) atomicExch(p.status, 1); akk = 1.f; }
-            rs_next = rsqrtf(akk);
+            const float dcand = fmaf(-lk, lk, a[k + 1]);  // valid in lane k+1: next pivot
+            const float akk = __shfl_sync(0xffffffffu, dcand, k + 1);
+            const bool bad = !(akk > 0.f);
+            bad_pivot |= bad;
+            rs_next = fast_rsqrt(bad ? 1.f : akk);
           }
           if (lane == k) rd[k] = rs;
-          a[k] = lk;
+          a[k] = lane >= k ? lk : 0.f;         // strict upper part of the factor is zero
           const float yk = __shfl_sync(0xffffffffu, b_reg, k) * rs;  // y_k = b_k / L_kk
           if (lane == k) b_reg = yk;
           else if (lane > k) b_reg = fmaf(-lk, yk, b_reg);
+          __syncwarp();
+          const float4* col = reinterpret_cast<const float4*>(LdT + k * 32);
 #pragma unroll
-          for (int j = k + 1; j < 32; ++j) {
-            const float skj = __shfl_sync(0xffffffffu, a[j], k);  // S[k][j] = S[j][k]
-            a[j] = fmaf(-t, skj, a[j]);
+          for (int m4 = (k + 1) / 4; m4 < 8; ++m4) {
+            const float4 c = col[m4];  // L[j][k], j = 4*m4 .. 4*m4+3
+            if (4 * m4 + 0 > k) a[4 * m4 + 0] = fmaf(-lk, c.x, a[4 * m4 + 0]);
+            if (4 * m4 + 1 > k) a[4 * m4 + 1] = fmaf(-lk, c.y, a[4 * m4 + 1]);
+            if (4 * m4 + 2 > k) a[4 * m4 + 2] = fmaf(-lk, c.z, a[4 * m4 + 2]);
+            if (4 * m4 + 3 > k) a[4 * m4 + 3] = fmaf(-lk, c.w, a[4 * m4 + 3]);
           }
           rs = rs_next;
         }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (j > lane) a[j] = 0.f;     // strict upper part of the factor
-          LdT[j * 32 + lane] = a[j];
-        }
         yS[lane] = b_reg;               // y_i of this row
+        if (bad_pivot && lane == 0) atomicExch(p.status, 1);
         if (p.dbg && lane == 0) atomicAdd(p.dbg + 10, (unsigned long long)(clock64() - dgt0));
       }
       __syncthreads();  // L11, 1/diag and y of the panel are visible
