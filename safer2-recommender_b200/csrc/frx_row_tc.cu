@@ -43,6 +43,29 @@ __device__ __forceinline__ float fast_rsqrt(float x) {
   return y;
 }
 
+// Packed fp32 pairs (FFMA2): a 3-register FFMA issues every other cycle per scheduler, so the in-register
+// triangular sweeps are FMA-issue bound; fma.rn.f32x2 does two IEEE fp32 FMAs per issue slot.
+__device__ __forceinline__ unsigned long long pack2(float x, float y) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+// (d0, d1) += a2 * (b0, b1)
+__device__ __forceinline__ void fma2(float& d0, float& d1, unsigned long long a2, float b0, float b1) {
+  asm("{\n\t.reg .b64 rb, rc;\n\tmov.b64 rb, {%3, %4};\n\tmov.b64 rc, {%0, %1};\n\t"
+      "fma.rn.f32x2 rc, %2, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "+f"(d0), "+f"(d1)
+      : "l"(a2), "f"(b0), "f"(b1));
+}
+// a[j..j+3] -= l * c for the entries with index > k (k is a compile-time constant after unrolling)
+#define FRX_SWEEP4(a, j, k, l, nl2, c)                               \
+  do {                                                               \
+    if ((j) > (k)) fma2(a[(j)], a[(j) + 1], nl2, c.x, c.y);          \
+    else if ((j) + 1 > (k)) a[(j) + 1] = fmaf(-(l), c.y, a[(j) + 1]); \
+    if ((j) + 2 > (k)) fma2(a[(j) + 2], a[(j) + 3], nl2, c.z, c.w);  \
+    else if ((j) + 3 > (k)) a[(j) + 3] = fmaf(-(l), c.w, a[(j) + 3]); \
+  } while (0)
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -454,9 +477,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
           if (k + 1 < 32) {
             const float dcand = fmaf(-lk, lk, a[k + 1]);  // valid in lane k+1: next pivot
             const float akk = __shfl_sync(0xffffffffu, dcand, k + 1);
-            const bool bad = !(akk > 0.f);
-            bad_pivot |= bad;
-            rs_next = fast_rsqrt(bad ? 1.f : akk);
+            bad_pivot |= !(akk > 0.f);                    // off the dependency chain; a bad pivot yields NaNs + status
+            rs_next = fast_rsqrt(akk);
+            // the next column is needed first: its update takes the shuffle shortcut instead of the
+            // shared-memory round trip, which then has two steps of slack
+            const float lnext = __shfl_sync(0xffffffffu, lk, k + 1);  // L[k+1][k]
+            a[k + 1] = fmaf(-lk, lnext, a[k + 1]);
           }
           if (lane == k) rd[k] = rs;
           a[k] = lane >= k ? lk : 0.f;         // strict upper part of the factor is zero
@@ -464,14 +490,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
           if (lane == k) b_reg = yk;
           else if (lane > k) b_reg = fmaf(-lk, yk, b_reg);
           __syncwarp();
+          const unsigned long long nlk2 = pack2(-lk, -lk);
           const float4* col = reinterpret_cast<const float4*>(LdT + k * 32);
 #pragma unroll
-          for (int m4 = (k + 1) / 4; m4 < 8; ++m4) {
+          for (int m4 = (k + 2) / 4; m4 < 8; ++m4) {
             const float4 c = col[m4];  // L[j][k], j = 4*m4 .. 4*m4+3
-            if (4 * m4 + 0 > k) a[4 * m4 + 0] = fmaf(-lk, c.x, a[4 * m4 + 0]);
-            if (4 * m4 + 1 > k) a[4 * m4 + 1] = fmaf(-lk, c.y, a[4 * m4 + 1]);
-            if (4 * m4 + 2 > k) a[4 * m4 + 2] = fmaf(-lk, c.z, a[4 * m4 + 2]);
-            if (4 * m4 + 3 > k) a[4 * m4 + 3] = fmaf(-lk, c.w, a[4 * m4 + 3]);
+            FRX_SWEEP4(a, 4 * m4, k + 1, lk, nlk2, c);
           }
           rs = rs_next;
         }
@@ -489,14 +513,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
         for (int k = 0; k < 32; ++k) {
           const float l = a[k] * rd[k];
           a[k] = l;
+          const unsigned long long nl2 = pack2(-l, -l);
           const float4* col = reinterpret_cast<const float4*>(LdT + k * 32);
 #pragma unroll
           for (int m4 = (k + 1) / 4; m4 < 8; ++m4) {
             const float4 c = col[m4];
-            if (4 * m4 + 0 > k) a[4 * m4 + 0] = fmaf(-l, c.x, a[4 * m4 + 0]);
-            if (4 * m4 + 1 > k) a[4 * m4 + 1] = fmaf(-l, c.y, a[4 * m4 + 1]);
-            if (4 * m4 + 2 > k) a[4 * m4 + 2] = fmaf(-l, c.z, a[4 * m4 + 2]);
-            if (4 * m4 + 3 > k) a[4 * m4 + 3] = fmaf(-l, c.w, a[4 * m4 + 3]);
+            FRX_SWEEP4(a, 4 * m4, k, l, nl2, c);
           }
         }
         const int i = 32 * warp + lane;
@@ -579,14 +601,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           x[j] *= rd[j];
+          const float xj = x[j];
+          const unsigned long long nx2 = pack2(-xj, -xj);
           const float4* col = reinterpret_cast<const float4*>(LdT + j * 32);
 #pragma unroll
           for (int m4 = (j + 1) / 4; m4 < 8; ++m4) {
             const float4 c = col[m4];
-            if (4 * m4 + 0 > j) x[4 * m4 + 0] = fmaf(-c.x, x[j], x[4 * m4 + 0]);
-            if (4 * m4 + 1 > j) x[4 * m4 + 1] = fmaf(-c.y, x[j], x[4 * m4 + 1]);
-            if (4 * m4 + 2 > j) x[4 * m4 + 2] = fmaf(-c.z, x[j], x[4 * m4 + 2]);
-            if (4 * m4 + 3 > j) x[4 * m4 + 3] = fmaf(-c.w, x[j], x[4 * m4 + 3]);
+            FRX_SWEEP4(x, 4 * m4, j, xj, nx2, c);
           }
         }
 #pragma unroll
