@@ -180,7 +180,7 @@ struct TcLayout {
   static constexpr int kYOff = kWsumOff + P * 32 * 4;     // y of the current panel [32]
   static constexpr int kRdOff = kYOff + 32 * 4;           // reciprocal diagonal of the current factor, [2][32]
   static constexpr int kBarOff = ((kRdOff + 2 * 32 * 4 + 15) / 16) * 16;
-  static constexpr int kTotal = kBarOff + 64;
+  static constexpr int kTotal = kBarOff + 128;
   static constexpr int kTmemCols = D == 256 ? 512 : 128;
   __host__ __device__ static constexpr int lst_off(int p) { return 32 * (p * D - 16 * p * (p - 1)); }
 };
@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
   uint64_t* empty_bar = bars + 2;  // [2]
   uint64_t* acc_bar = bars + 4;    // [1] SYRK accumulators complete
   uint64_t* upd_bar = bars + 5;    // [1] trailing update complete
+  uint64_t* col_bar = bars + 6;    // [4] columns 8q..8q+7 of the current diagonal factor are published
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
     mbar_init(&empty_bar[1], 1);
     mbar_init(acc_bar, 1);
     mbar_init(upd_bar, 1);
+    for (int q = 0; q < 4; ++q) mbar_init(&col_bar[q], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == TC_LOADER_WARPS) {
@@ -498,19 +500,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
             FRX_SWEEP4(a, 4 * m4, k + 1, lk, nlk2, c);
           }
           rs = rs_next;
+          if ((k & 7) == 7) {
+            // the rows below run their triangular solve behind this sweep, eight columns at a time
+            if (k == 31) yS[lane] = b_reg;  // y_i of this row
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&col_bar[k >> 3]);
+          }
         }
-        yS[lane] = b_reg;               // y_i of this row
         if (bad_pivot && lane == 0) atomicExch(p.status, 1);
         if (p.dbg && lane == 0) atomicAdd(p.dbg + 10, (unsigned long long)(clock64() - dgt0));
       }
-      __syncthreads();  // L11, 1/diag and y of the panel are visible
-      FRX_DBG_LAP(3);  // panel load + diagonal block factor (barrier wait lands in the next lap: BAR is deferred-blocking)
+      FRX_DBG_LAP(3);  // panel load (+ the diagonal block factor in the diagonal warp)
       if (is_row_warp && warp > pn) {
         // -- rows below: L21 row by forward substitution against L11 (column sweep, in place) --
         long long trt0 = 0;
-        if (p.dbg && warp == P - 1 && lane == 0) { volatile float probe = rd[0]; (void)probe; trt0 = clock64(); }
+        if (p.dbg && warp == P - 1 && lane == 0) trt0 = clock64();
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
+          // one arrival per panel on each column barrier and P is even: the phase parity is the panel parity
+          if ((k & 7) == 0) mbar_wait(&col_bar[k >> 3], (uint32_t)(pn & 1));
           const float l = a[k] * rd[k];
           a[k] = l;
           const unsigned long long nl2 = pack2(-l, -l);
@@ -618,45 +626,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
     __syncthreads();
 
     // ---- back substitution L^T x = y, panel by panel from the bottom; b_reg: y_i -> x_i ----
+    // Thread k owns COLUMN k of L here: element (i, k) of a stored panel row sits at word
+    // i*32 + swz(k, i), so the 32 lanes of a warp read one row conflict-free.  Warp pn first applies
+    // inv(L11)^T to its residuals (32 terms), publishes x, then the warps above subtract the 32 new terms.
+    float* xS = wsum;  // x_i of the solved panels, [D]
 #pragma unroll 1
     for (int pn = P - 1; pn >= 0; --pn) {
-      const int c0 = 32 * pn;
-      const float* Lp = Lst + L::lst_off(pn);
-      if (is_row_warp && warp > pn) {
-        const int i = 32 * warp + lane;
-        const float4* src = reinterpret_cast<const float4*>(Lp + (size_t)(i - c0) * 32);
-        float part[32];
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          const float4 l4 = src[(c4 ^ (lane & 7)) & 7];
-          part[4 * c4] = l4.x * b_reg;
-          part[4 * c4 + 1] = l4.y * b_reg;
-          part[4 * c4 + 2] = l4.z * b_reg;
-          part[4 * c4 + 3] = l4.w * b_reg;
-        }
-        transpose_reduce<32>(part, lane);
-        wsum[warp * 32 + lane] = part[0];
-      }
-      __syncthreads();
       if (warp == pn) {
-        float rk = b_reg;
-        for (int w2 = pn + 1; w2 < P; ++w2) rk -= wsum[w2 * 32 + lane];
-        // x_k = sum_{j >= k} inv(L11)[j][k] * r_j: lane j scales row j of inv(L11), column sums by transpose-reduce
-        float pr[32];
-        const float4* lrow = reinterpret_cast<const float4*>(Lp + lane * 32);
+        const float* Lp = Lst + L::lst_off(pn);
+        yS[lane] = b_reg;  // residual r_j of this panel
+        __syncwarp();
+        float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          const float4 l4 = lrow[(c4 ^ (lane & 7)) & 7];
-          pr[4 * c4] = l4.x * rk;
-          pr[4 * c4 + 1] = l4.y * rk;
-          pr[4 * c4 + 2] = l4.z * rk;
-          pr[4 * c4 + 3] = l4.w * rk;
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 r4 = reinterpret_cast<const float4*>(yS)[j4];
+          const int j = 4 * j4;  // inv(L11)[j][lane]; exact zeros above the diagonal
+          x0 = fmaf(Lp[(j + 0) * 32 + ((((lane >> 2) ^ ((j + 0) & 7)) & 7) << 2) + (lane & 3)], r4.x, x0);
+          x1 = fmaf(Lp[(j + 1) * 32 + ((((lane >> 2) ^ ((j + 1) & 7)) & 7) << 2) + (lane & 3)], r4.y, x1);
+          x2 = fmaf(Lp[(j + 2) * 32 + ((((lane >> 2) ^ ((j + 2) & 7)) & 7) << 2) + (lane & 3)], r4.z, x2);
+          x3 = fmaf(Lp[(j + 3) * 32 + ((((lane >> 2) ^ ((j + 3) & 7)) & 7) << 2) + (lane & 3)], r4.w, x3);
         }
-        transpose_reduce<32>(pr, lane);
-        const float xk = pr[0];
-        b_reg = xk;
+        b_reg = (x0 + x1) + (x2 + x3);
+        xS[32 * pn + lane] = b_reg;
       }
       __syncthreads();
+      if (is_row_warp && warp < pn) {
+        // rows [32 pn, 32 pn + 32) of this warp's own column panel
+        const float* Lw = Lst + L::lst_off(warp) + (size_t)(32 * (pn - warp)) * 32;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int t4 = 0; t4 < 8; ++t4) {
+          const float4 x4 = reinterpret_cast<const float4*>(xS + 32 * pn)[t4];
+          const int t = 4 * t4;  // (32 pn + t) & 7 == t & 7
+          s0 = fmaf(Lw[(t + 0) * 32 + ((((lane >> 2) ^ ((t + 0) & 7)) & 7) << 2) + (lane & 3)], x4.x, s0);
+          s1 = fmaf(Lw[(t + 1) * 32 + ((((lane >> 2) ^ ((t + 1) & 7)) & 7) << 2) + (lane & 3)], x4.y, s1);
+          s2 = fmaf(Lw[(t + 2) * 32 + ((((lane >> 2) ^ ((t + 2) & 7)) & 7) << 2) + (lane & 3)], x4.z, s2);
+          s3 = fmaf(Lw[(t + 3) * 32 + ((((lane >> 2) ^ ((t + 3) & 7)) & 7) << 2) + (lane & 3)], x4.w, s3);
+        }
+        b_reg -= (s0 + s1) + (s2 + s3);
+      }
     }
     if (is_row_warp) p.X[(size_t)xr * D + 32 * warp + lane] = b_reg;
     tc_fence_before();
