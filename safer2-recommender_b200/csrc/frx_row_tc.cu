@@ -30,8 +30,9 @@ namespace frx {
 
 namespace {
 
-constexpr int TC_LOADER_WARPS = 16;                     // 2 groups of 8
-constexpr int TC_THREADS = (TC_LOADER_WARPS + 1) * 32;  // + 1 MMA-issuing warp
+constexpr int TC_LOADER_WARPS = 16;               // 2 groups of 8
+constexpr int TC_THREADS = TC_LOADER_WARPS * 32;  // 4 warps per scheduler -> 128 registers per thread
+constexpr int TC_MMA_WARP = 15;                   // owns TMEM and issues the trailing updates
 constexpr int KT = 32;                                  // entries per operand tile (128 B rows) = panel width
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -180,10 +181,88 @@ struct TcLayout {
   static constexpr int kYOff = kWsumOff + P * 32 * 4;     // y of the current panel [32]
   static constexpr int kRdOff = kYOff + 32 * 4;           // reciprocal diagonal of the current factor, [2][32]
   static constexpr int kBarOff = ((kRdOff + 2 * 32 * 4 + 15) / 16) * 16;
-  static constexpr int kTotal = kBarOff + 128;
+  // G staging for tmem_init_system, 4 KB per warp: aliases operand stage 0 when that holds 64 KB (D = 256)
+  static constexpr int kGbufOff = kStageBytes >= TC_LOADER_WARPS * 4096 ? 0 : kBarOff + 128;
+  static constexpr int kTotal = kGbufOff == 0 ? kBarOff + 128 : kGbufOff + TC_LOADER_WARPS * 4096;
   static constexpr int kTmemCols = D == 256 ? 512 : 128;
   __host__ __device__ static constexpr int lst_off(int p) { return 32 * (p * D - 16 * p * (p - 1)); }
 };
+
+// Per-row scalars.  The system handed to the Cholesky is  S + alpha*G + beta*I  with S the tensor-core
+// SYRK sum and rhs * bscale on the right: for the user form (safer2.h:143-150) that is the reference's
+// w*(S/n + uw*G) + reg*I and rhs*w/n multiplied through by n/w, which leaves the solution unchanged and
+// lets alpha*G + beta*I be written into TMEM BEFORE the SYRK accumulates on top of it.
+struct RowScalars {
+  float alpha, beta, bscale;
+};
+__device__ __forceinline__ RowScalars row_scalars(const RowParams& p, int r, int n) {
+  RowScalars s;
+  s.bscale = 1.f;
+  if (p.mode == RM_IALS) {  // ials.h:101-105
+    s.alpha = p.uw;
+    s.beta = (float)((double)p.reg * pow((double)((float)n + p.uw * (float)p.num_other), (double)p.reg_exp));
+  } else if (p.mode == RM_SAFER_V) {  // safer2.h:176,206-208
+    s.alpha = p.uw;
+    s.beta = p.reg * (p.item_reg[r] + p.alpha * p.uw * (float)p.num_users_total);
+  } else {
+    const float reg = p.reg * (1.f + p.uw * (float)p.num_other);
+    const float w = p.row_w ? p.row_w[r] : 1.f;
+    if (w > 0.f) {
+      s.alpha = (float)n * p.uw;
+      s.beta = (float)n * reg / w;
+    } else {  // reference system degenerates to reg*I x = 0
+      s.alpha = 0.f;
+      s.beta = 1.f;
+      s.bscale = 0.f;
+    }
+  }
+  return s;
+}
+
+// TMEM <- alpha*G + beta*I on the lower-triangle 32x32 chunks of the d x d accumulator.  Run by the
+// `nshare` warps that share TMEM lane quarter `rq` (share id `sid`); `gbuf` is a private 4 KB buffer:
+// G rows arrive as coalesced 128 B segments, are stored XOR-swizzled and read back row-per-lane.
+template <int D>
+__device__ __forceinline__ void tmem_init_system(const float* __restrict__ G, float alpha, float beta, uint32_t tmem_base,
+                                                 int rq, int sid, int nshare, float* gbuf, int lane) {
+  constexpr int NB = D / 128;
+  const int per_rb0 = rq + 1;                       // chunks with j <= i for M block 0
+  const int total = NB == 2 ? 2 * rq + 6 : rq + 1;  // (rq + 1) + (4 + rq + 1)
+  float4 gv[8];
+  auto fetch = [&](int c) {
+    const int rb = c < per_rb0 ? 0 : 1, ch = c < per_rb0 ? c : c - per_rb0;
+    const float* gblk = G + (size_t)(128 * rb + 32 * rq) * D + 32 * ch;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) gv[it] = __ldg(reinterpret_cast<const float4*>(gblk + (size_t)(it * 4 + (lane >> 3)) * D) + (lane & 7));
+  };
+  if (sid < total) fetch(sid);
+  for (int c = sid; c < total; c += nshare) {
+    const int rb = c < per_rb0 ? 0 : 1, ch = c < per_rb0 ? c : c - per_rb0;
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = it * 4 + (lane >> 3), c16 = lane & 7;
+      *reinterpret_cast<float4*>(gbuf + row * 32 + ((c16 ^ (row & 7)) << 2)) = gv[it];
+    }
+    __syncwarp();
+    if (c + nshare < total) fetch(c + nshare);  // next chunk's G is in flight while this one is written
+    uint32_t u[32];
+    const bool diag_chunk = (4 * rb + rq) == ch;
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+      const float4 g4 = *reinterpret_cast<const float4*>(gbuf + lane * 32 + ((c4 ^ (lane & 7)) << 2));
+      const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+      for (int t4 = 0; t4 < 4; ++t4) {
+        float m = alpha * gg[t4];
+        if (diag_chunk && 4 * c4 + t4 == lane) m += beta;
+        u[4 * c4 + t4] = __float_as_uint(m);
+      }
+    }
+    FRX_TMEM_ST32(tmem_base + ((uint32_t)(32 * rq) << 16) + (rb ? 256u : 0u) + (uint32_t)(32 * ch), u);
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 
 template <int D>
 __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p) {
@@ -209,6 +288,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
   uint64_t* acc_bar = bars + 4;    // [1] SYRK accumulators complete
   uint64_t* upd_bar = bars + 5;    // [1] trailing update complete
   uint64_t* col_bar = bars + 6;    // [4] columns 8q..8q+7 of the current diagonal factor are published
+  uint64_t* order_bar = bars + 10; // [2] SYRK issuer g has issued another tile (keeps the two issuers in tile order)
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -221,12 +301,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
     mbar_init(&full_bar[1], 8);
     mbar_init(&empty_bar[0], 1);
     mbar_init(&empty_bar[1], 1);
-    mbar_init(acc_bar, 1);
+    mbar_init(acc_bar, 2);  // one arrival per SYRK issuer
+    mbar_init(&order_bar[0], 1);
+    mbar_init(&order_bar[1], 1);
     mbar_init(upd_bar, 1);
     for (int q = 0; q < 4; ++q) mbar_init(&col_bar[q], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == TC_LOADER_WARPS) {
+  if (warp == TC_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(L::kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
@@ -239,8 +321,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
   const int rq = warp & 3, rb = (D == 256) ? ((warp >> 2) & 1) : 0;
   const uint32_t trow = tmem_base + ((uint32_t)(32 * rq) << 16) + (rb ? 256u : 0u);
 
+  // alpha*G + beta*I of the first row; for the later rows the warps that are idle during the back
+  // substitution of the previous row do it (TMEM is free again by then)
+  float* gbuf = reinterpret_cast<float*>(sm + L::kGbufOff) + warp * 1024;
+  if ((int)blockIdx.x < p.num_rows) {
+    const int r0 = p.order[blockIdx.x];
+    const RowScalars s0 = row_scalars(p, r0, p.ptr[r0 + 1] - p.ptr[r0]);
+    tmem_init_system<D>(p.G, s0.alpha, s0.beta, tmem_base, warp & 3, warp >> 2, 4, gbuf, lane);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
   uint32_t loader_use = 0;          // tiles this loader group has staged so far (all rows)
-  uint32_t mma_use[2] = {0u, 0u};   // tiles consumed per stage (all rows)
+  uint32_t other_use = 0;           // tiles the OTHER loader group has staged in the previous rows
   uint32_t row_count = 0;
   uint32_t upd_count = 0;           // trailing-update commits so far (all rows)
   unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -260,9 +354,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
       dup_hi = 128 * kf;
     }
 
-    if (warp < TC_LOADER_WARPS) {
+    {
       // ================= loaders: gather, split, transpose into the operand tiles =================
       const int g = warp >> 3, wg = warp & 7;
+      constexpr uint32_t idesc_n128 = make_idesc_tf32(128);
+      constexpr uint32_t idesc_n256 = make_idesc_tf32(256);
       const int slab = wg * C;  // first feature this warp handles
       float rhs_acc = 0.f;
       const uint32_t kq = (uint32_t)(lane >> 2), kr = (uint32_t)(lane & 3) << 2;
@@ -308,46 +404,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_bar[g]);
         ++loader_use;
+        if (wg == 0) {
+          // ---- the first warp of each group issues the SYRK MMAs of its group's stage; the two issuers
+          //      alternate tile by tile, kept in order by order_bar (fence + arrive / wait + fence) ----
+          mbar_wait(&full_bar[g], (loader_use - 1) & 1);
+          if (t > 0) mbar_wait(&order_bar[g ^ 1], (other_use + (uint32_t)((t - 1) >> 1)) & 1);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t hi_addr = sm_addr + g * L::kStageBytes;
+            const uint32_t lo_addr = hi_addr + L::kTileBytes;
+#pragma unroll
+            for (int ks = 0; ks < KT / 8; ++ks) {
+              const uint32_t ko = ks * 32;
+              const uint64_t b_hi = make_kmajor_desc(hi_addr + ko);
+              const uint64_t b_lo = make_kmajor_desc(lo_addr + ko);
+              {  // rows 0..127 x cols 0..127 -> TMEM columns [0,128); accumulates onto alpha*G + beta*I
+                umma_tf32(tmem_base, b_hi, b_hi, idesc_n128, 1u);
+                umma_tf32(tmem_base, b_hi, b_lo, idesc_n128, 1u);
+                umma_tf32(tmem_base, b_lo, b_hi, idesc_n128, 1u);
+              }
+              if (D == 256) {  // rows 128..255 x cols 0..255 -> TMEM columns [256,512)
+                const uint64_t a_hi = make_kmajor_desc(hi_addr + 128 * 128 + ko);
+                const uint64_t a_lo = make_kmajor_desc(lo_addr + 128 * 128 + ko);
+                umma_tf32(tmem_base + 256, a_hi, b_hi, idesc_n256, 1u);
+                umma_tf32(tmem_base + 256, a_hi, b_lo, idesc_n256, 1u);
+                umma_tf32(tmem_base + 256, a_lo, b_hi, idesc_n256, 1u);
+              }
+            }
+            umma_commit(&empty_bar[g]);
+            if (t + 2 >= T) umma_commit(acc_bar);  // this group's last tile of the row
+            tc_fence_before();
+            mbar_arrive(&order_bar[g]);
+          }
+          __syncwarp();
+        }
         transpose_reduce<C>(rv, lane);
         rhs_acc += rv[0];
       }
+      if (wg == 0 && g >= T && lane == 0) mbar_arrive(acc_bar);  // no tile for this issuer in this row
+      other_use += (uint32_t)((T + g) >> 1);  // the other group: group 0 stages ceil(T/2) tiles, group 1 floor(T/2)
       if (C == 32 || (lane & 1) == 0) rhs_part[g * D + slab + (C == 32 ? lane : (lane >> 1))] = rhs_acc;
-    } else {
-      // ================= MMA issuer: SYRK =================
-      constexpr uint32_t idesc_n128 = make_idesc_tf32(128);
-      constexpr uint32_t idesc_n256 = make_idesc_tf32(256);
-      for (int t = 0; t < T; ++t) {
-        const int s = t & 1;
-        mbar_wait(&full_bar[s], mma_use[s] & 1);
-        ++mma_use[s];
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t hi_addr = sm_addr + s * L::kStageBytes;
-          const uint32_t lo_addr = hi_addr + L::kTileBytes;
-#pragma unroll
-          for (int ks = 0; ks < KT / 8; ++ks) {
-            const uint32_t ko = ks * 32;
-            const uint64_t b_hi = make_kmajor_desc(hi_addr + ko);
-            const uint64_t b_lo = make_kmajor_desc(lo_addr + ko);
-            const uint32_t first = (t == 0 && ks == 0) ? 0u : 1u;
-            {  // rows 0..127 x cols 0..127 -> TMEM columns [0,128)
-              umma_tf32(tmem_base, b_hi, b_hi, idesc_n128, first);
-              umma_tf32(tmem_base, b_hi, b_lo, idesc_n128, 1u);
-              umma_tf32(tmem_base, b_lo, b_hi, idesc_n128, 1u);
-            }
-            if (D == 256) {  // rows 128..255 x cols 0..255 -> TMEM columns [256,512)
-              const uint64_t a_hi = make_kmajor_desc(hi_addr + 128 * 128 + ko);
-              const uint64_t a_lo = make_kmajor_desc(lo_addr + 128 * 128 + ko);
-              umma_tf32(tmem_base + 256, a_hi, b_hi, idesc_n256, first);
-              umma_tf32(tmem_base + 256, a_hi, b_lo, idesc_n256, 1u);
-              umma_tf32(tmem_base + 256, a_lo, b_hi, idesc_n256, 1u);
-            }
-          }
-          umma_commit(&empty_bar[s]);
-          if (t == T - 1) umma_commit(acc_bar);
-        }
-        __syncwarp();
-      }
     }
 
     // ================= phase B =================
@@ -356,81 +452,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
     __syncthreads();  // rhs_part visible; all operand tiles consumed -> the staging area may be reused
     FRX_DBG_LAP(0);  // phase A (gather + SYRK)
 
-    // ---- per-row scalars (same formulas as the generic kernel) ----
-    float reg, weight = 1.f;
-    if (mode == RM_IALS) {
-      reg = (float)((double)p.reg * pow((double)((float)n + p.uw * (float)p.num_other), (double)p.reg_exp));
-    } else if (item_side) {
-      reg = p.reg * (p.item_reg[r] + p.alpha * p.uw * (float)p.num_users_total);
-    } else {
-      reg = p.reg * (1.f + p.uw * (float)p.num_other);
-      weight = p.row_w ? p.row_w[r] : 1.f;
-    }
-    const bool user_form = (mode == RM_SAFER_U);
-    const float nf = (float)n;
-    const float inv_nf = 1.f / nf;
-
-    // ---- assemble M = a*A + b*G + reg*I in TMEM (lower part incl. the diagonal 32-blocks) ----
-    if (warp < 16 && (D == 256 || ((warp >> 2) & 1) == 0 || D == 128)) {
-      const int split = (D == 256) ? (warp >> 3) : (warp >> 2);
-      constexpr int nsplit = (D == 256) ? 2 : 4;
-      const int i = 128 * rb + 32 * rq + lane;
-      const int nch = 4 * rb + rq + 1;  // 32-column chunks covering j <= i for the whole warp
-      // G block [32 rows of this warp][32 columns] is fetched with coalesced 128 B row segments into a
-      // private, XOR-swizzled 4 KB buffer (the operand-tile area is idle here), then read row-per-lane.
-      float* gbuf = reinterpret_cast<float*>(sm) + warp * 1024;
-      const float* gblk = p.G + (size_t)(128 * rb + 32 * rq) * D;
-      for (int ch = split; ch < nch; ch += nsplit) {
-        uint32_t u[32];
-        FRX_TMEM_LD32(u, trow + (uint32_t)(32 * ch));
-        __syncwarp();
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int row = it * 4 + (lane >> 3), c16 = lane & 7;
-          const float4 gv = __ldg(reinterpret_cast<const float4*>(gblk + (size_t)row * D + 32 * ch) + c16);
-          *reinterpret_cast<float4*>(gbuf + row * 32 + ((c16 ^ (row & 7)) << 2)) = gv;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          const float4 gv = *reinterpret_cast<const float4*>(gbuf + lane * 32 + ((c4 ^ (lane & 7)) << 2));
-          const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
-#pragma unroll
-          for (int t4 = 0; t4 < 4; ++t4) {
-            const int jj = 4 * c4 + t4;
-            const int j = 32 * ch + jj;
-            const float sij = __uint_as_float(u[jj]);
-            float m;
-            if (user_form) {  // safer2.h:143-150
-              m = sij * inv_nf;  // reference divides (safer2.h:143); 1 ulp apart, far inside the tolerance
-              m += p.uw * gg[t4];
-              m *= weight;
-              if (i == j) m += reg;
-            } else if (mode == RM_IALS) {  // ials.h:101-105
-              m = p.uw * gg[t4];
-              if (i == j) m += reg;
-              m += sij;
-            } else {  // safer2.h:176,206-208
-              m = p.uw * gg[t4] + sij;
-              if (i == j) m += reg;
-            }
-            u[jj] = __float_as_uint(m);
-          }
-        }
-        FRX_TMEM_ST32(trow + (uint32_t)(32 * ch), u);
-      }
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    }
+    const RowScalars rs_row = row_scalars(p, r, n);
     float b_reg = 0.f;  // this row-thread's rhs element, then y_i, then x_i
     if (is_row_warp) {
       const int i = 32 * warp + lane;
-      const float sc = user_form ? weight / nf : 1.f;
-      b_reg = (rhs_part[i] + rhs_part[D + i]) * sc;
+      b_reg = (rhs_part[i] + rhs_part[D + i]) * rs_row.bscale;
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    FRX_DBG_LAP(1);  // assemble
+    FRX_DBG_LAP(1);  // rhs
 
     // ---- blocked Cholesky, 32-wide panels ----
 #pragma unroll 1
@@ -568,7 +599,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
         tc_fence_before();
         __syncthreads();
         FRX_DBG_LAP(4);  // TRSM + operand tiles
-        if (warp == TC_LOADER_WARPS) {
+        if (warp == TC_MMA_WARP) {
           tc_fence_after();
           if (lane == 0) {
             // A22 -= L21 L21^T on columns [c1, limit) of every M block that still has rows >= c1
@@ -623,6 +654,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
           Lp[i2 * 32 + ((((lane >> 2) ^ (i2 & 7)) & 7) << 2) + (lane & 3)] = x[i2];  // lane c holds column c
       }
     }
+    tc_fence_before();  // the last panel has been read from TMEM
     __syncthreads();
 
     // ---- back substitution L^T x = y, panel by panel from the bottom; b_reg: y_i -> x_i ----
@@ -630,8 +662,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
     // i*32 + swz(k, i), so the 32 lanes of a warp read one row conflict-free.  Warp pn first applies
     // inv(L11)^T to its residuals (32 terms), publishes x, then the warps above subtract the 32 new terms.
     float* xS = wsum;  // x_i of the solved panels, [D]
+    if (!is_row_warp) {
+      // meanwhile the other warps write alpha*G + beta*I of this CTA's NEXT row into the idle TMEM
+      const int rin = ri + (int)gridDim.x;
+      if (rin < p.num_rows) {
+        const int rn = p.order[rin];
+        const RowScalars sn = row_scalars(p, rn, p.ptr[rn + 1] - p.ptr[rn]);
+        constexpr int nshare = (TC_LOADER_WARPS - P) / 4;
+        tc_fence_after();
+        tmem_init_system<D>(p.G, sn.alpha, sn.beta, tmem_base, warp & 3, (warp - P) >> 2, nshare,
+                            gbuf, lane);
+      }
+    }
 #pragma unroll 1
-    for (int pn = P - 1; pn >= 0; --pn) {
+    for (int pn = P - 1; is_row_warp && pn >= 0; --pn) {
       if (warp == pn) {
         const float* Lp = Lst + L::lst_off(pn);
         yS[lane] = b_reg;  // residual r_j of this panel
@@ -649,8 +693,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
         b_reg = (x0 + x1) + (x2 + x3);
         xS[32 * pn + lane] = b_reg;
       }
-      __syncthreads();
-      if (is_row_warp && warp < pn) {
+      asm volatile("bar.sync 1, %0;" ::"n"(P * 32) : "memory");  // row warps only
+      if (warp < pn) {
         // rows [32 pn, 32 pn + 32) of this warp's own column panel
         const float* Lw = Lst + L::lst_off(warp) + (size_t)(32 * (pn - warp)) * 32;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -678,7 +722,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
   if (p.dbg && tid == 0) atomicAdd(p.dbg + 6, (unsigned long long)row_count);
   tc_fence_before();
   __syncthreads();
-  if (warp == TC_LOADER_WARPS)
+  if (warp == TC_MMA_WARP)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(L::kTmemCols));
 }
 
