@@ -288,7 +288,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
   uint64_t* acc_bar = bars + 4;    // [1] SYRK accumulators complete
   uint64_t* upd_bar = bars + 5;    // [1] trailing update complete
   uint64_t* col_bar = bars + 6;    // [4] columns 8q..8q+7 of the current diagonal factor are published
-  uint64_t* order_bar = bars + 10; // [2] SYRK issuer g has issued another tile (keeps the two issuers in tile order)
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -301,9 +300,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
     mbar_init(&full_bar[1], 8);
     mbar_init(&empty_bar[0], 1);
     mbar_init(&empty_bar[1], 1);
-    mbar_init(acc_bar, 2);  // one arrival per SYRK issuer
-    mbar_init(&order_bar[0], 1);
-    mbar_init(&order_bar[1], 1);
+    mbar_init(acc_bar, 1);
     mbar_init(upd_bar, 1);
     for (int q = 0; q < 4; ++q) mbar_init(&col_bar[q], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -333,8 +330,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
   __syncthreads();
   tc_fence_after();
 
-  uint32_t loader_use = 0;          // tiles this loader group has staged so far (all rows)
-  uint32_t other_use = 0;           // tiles the OTHER loader group has staged in the previous rows
+  uint32_t tile_base = 0;           // operand tiles of the rows this CTA has finished
   uint32_t row_count = 0;
   uint32_t upd_count = 0;           // trailing-update commits so far (all rows)
   unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -354,15 +350,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
       dup_hi = 128 * kf;
     }
 
-    {
+    const uint32_t row_tile0 = tile_base;  // CTA-wide index of this row's first tile: stage = index & 1
+    constexpr int SL = D / C;              // 32-entry x C-feature units per tile (8)
+    float rhs_acc[SL];
+#pragma unroll
+    for (int q = 0; q < SL; ++q) rhs_acc[q] = 0.f;
+    if (warp != TC_MMA_WARP) {
       // ================= loaders: gather, split, transpose into the operand tiles =================
-      const int g = warp >> 3, wg = warp & 7;
-      constexpr uint32_t idesc_n128 = make_idesc_tf32(128);
-      constexpr uint32_t idesc_n256 = make_idesc_tf32(256);
-      const int slab = wg * C;  // first feature this warp handles
-      float rhs_acc = 0.f;
+      // The 15 loader warps take the (tile, feature slab) units of the row round-robin; a stage is full
+      // after eight unit arrivals.  (The MMA-issuing thread blocks for most of a tile's MMA time, so it
+      // cannot double as a loader without delaying its group's next tile.)
       const uint32_t kq = (uint32_t)(lane >> 2), kr = (uint32_t)(lane & 3) << 2;
-      for (int t = g; t < T; t += 2) {
+      for (int u = warp; u < SL * T; u += TC_LOADER_WARPS - 1) {
+        const int t = u / SL, w8 = u % SL;
+        const int slab = w8 * C;  // first feature of this unit
         const int e = t * KT + lane;
         const bool valid = e < n;
         float4 v[F4];
@@ -381,8 +382,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
 #pragma unroll
           for (int j = 0; j < F4; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (loader_use > 0) mbar_wait(&empty_bar[g], (loader_use - 1) & 1);  // stage free again
-        uint8_t* hi_tile = sm + g * L::kStageBytes;
+        const uint32_t gt = row_tile0 + (uint32_t)t;
+        const int st = (int)(gt & 1u);
+        const uint32_t use = gt >> 1;  // earlier tiles of this stage
+        if (use > 0) mbar_wait(&empty_bar[st], (use - 1) & 1);  // stage free again
+        uint8_t* hi_tile = sm + st * L::kStageBytes;
         uint8_t* lo_tile = hi_tile + L::kTileBytes;
         float rv[C];
 #pragma unroll
@@ -402,61 +406,71 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(&full_bar[g]);
-        ++loader_use;
-        if (wg == 0) {
-          // ---- the first warp of each group issues the SYRK MMAs of its group's stage; the two issuers
-          //      alternate tile by tile, kept in order by order_bar (fence + arrive / wait + fence) ----
-          mbar_wait(&full_bar[g], (loader_use - 1) & 1);
-          if (t > 0) mbar_wait(&order_bar[g ^ 1], (other_use + (uint32_t)((t - 1) >> 1)) & 1);
-          tc_fence_after();
-          if (lane == 0) {
-            const uint32_t hi_addr = sm_addr + g * L::kStageBytes;
-            const uint32_t lo_addr = hi_addr + L::kTileBytes;
-#pragma unroll
-            for (int ks = 0; ks < KT / 8; ++ks) {
-              const uint32_t ko = ks * 32;
-              const uint64_t b_hi = make_kmajor_desc(hi_addr + ko);
-              const uint64_t b_lo = make_kmajor_desc(lo_addr + ko);
-              {  // rows 0..127 x cols 0..127 -> TMEM columns [0,128); accumulates onto alpha*G + beta*I
-                umma_tf32(tmem_base, b_hi, b_hi, idesc_n128, 1u);
-                umma_tf32(tmem_base, b_hi, b_lo, idesc_n128, 1u);
-                umma_tf32(tmem_base, b_lo, b_hi, idesc_n128, 1u);
-              }
-              if (D == 256) {  // rows 128..255 x cols 0..255 -> TMEM columns [256,512)
-                const uint64_t a_hi = make_kmajor_desc(hi_addr + 128 * 128 + ko);
-                const uint64_t a_lo = make_kmajor_desc(lo_addr + 128 * 128 + ko);
-                umma_tf32(tmem_base + 256, a_hi, b_hi, idesc_n256, 1u);
-                umma_tf32(tmem_base + 256, a_hi, b_lo, idesc_n256, 1u);
-                umma_tf32(tmem_base + 256, a_lo, b_hi, idesc_n256, 1u);
-              }
-            }
-            umma_commit(&empty_bar[g]);
-            if (t + 2 >= T) umma_commit(acc_bar);  // this group's last tile of the row
-            tc_fence_before();
-            mbar_arrive(&order_bar[g]);
-          }
-          __syncwarp();
-        }
+        if (lane == 0) mbar_arrive(&full_bar[st]);
         transpose_reduce<C>(rv, lane);
-        rhs_acc += rv[0];
+#pragma unroll
+        for (int q = 0; q < SL; ++q) rhs_acc[q] += (q == w8) ? rv[0] : 0.f;
       }
-      if (wg == 0 && g >= T && lane == 0) mbar_arrive(acc_bar);  // no tile for this issuer in this row
-      other_use += (uint32_t)((T + g) >> 1);  // the other group: group 0 stages ceil(T/2) tiles, group 1 floor(T/2)
-      if (C == 32 || (lane & 1) == 0) rhs_part[g * D + slab + (C == 32 ? lane : (lane >> 1))] = rhs_acc;
+    } else {
+      // ================= MMA issuer: SYRK, tiles in order =================
+      constexpr uint32_t idesc_n128 = make_idesc_tf32(128);
+      constexpr uint32_t idesc_n256 = make_idesc_tf32(256);
+      for (int t = 0; t < T; ++t) {
+        const uint32_t gt = row_tile0 + (uint32_t)t;
+        const int st = (int)(gt & 1u);
+        mbar_wait(&full_bar[st], (gt >> 1) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t hi_addr = sm_addr + st * L::kStageBytes;
+          const uint32_t lo_addr = hi_addr + L::kTileBytes;
+#pragma unroll
+          for (int ks = 0; ks < KT / 8; ++ks) {
+            const uint32_t ko = ks * 32;
+            const uint64_t b_hi = make_kmajor_desc(hi_addr + ko);
+            const uint64_t b_lo = make_kmajor_desc(lo_addr + ko);
+            {  // rows 0..127 x cols 0..127 -> TMEM columns [0,128); accumulates onto alpha*G + beta*I
+              umma_tf32(tmem_base, b_hi, b_hi, idesc_n128, 1u);
+              umma_tf32(tmem_base, b_hi, b_lo, idesc_n128, 1u);
+              umma_tf32(tmem_base, b_lo, b_hi, idesc_n128, 1u);
+            }
+            if (D == 256) {  // rows 128..255 x cols 0..255 -> TMEM columns [256,512)
+              const uint64_t a_hi = make_kmajor_desc(hi_addr + 128 * 128 + ko);
+              const uint64_t a_lo = make_kmajor_desc(lo_addr + 128 * 128 + ko);
+              umma_tf32(tmem_base + 256, a_hi, b_hi, idesc_n256, 1u);
+              umma_tf32(tmem_base + 256, a_hi, b_lo, idesc_n256, 1u);
+              umma_tf32(tmem_base + 256, a_lo, b_hi, idesc_n256, 1u);
+            }
+          }
+          umma_commit(&empty_bar[st]);
+          if (t == T - 1) umma_commit(acc_bar);
+        }
+        __syncwarp();
+      }
     }
+    tile_base += (uint32_t)T;
 
     // ================= phase B =================
-    mbar_wait(acc_bar, row_count & 1);
+    mbar_wait(acc_bar, row_count & 1);  // all operand tiles consumed -> the staging area may be reused
     tc_fence_after();
-    __syncthreads();  // rhs_part visible; all operand tiles consumed -> the staging area may be reused
+    {
+      // per-warp rhs partials go through the (now idle) staging area and are summed in a fixed order
+      float* part = reinterpret_cast<float*>(sm) + warp * D;
+      if (warp != TC_MMA_WARP && (C == 32 || (lane & 1) == 0)) {
+#pragma unroll
+        for (int q = 0; q < SL; ++q) part[q * C + (C == 32 ? lane : (lane >> 1))] = rhs_acc[q];
+      }
+    }
+    __syncthreads();
     FRX_DBG_LAP(0);  // phase A (gather + SYRK)
 
     const RowScalars rs_row = row_scalars(p, r, n);
     float b_reg = 0.f;  // this row-thread's rhs element, then y_i, then x_i
     if (is_row_warp) {
       const int i = 32 * warp + lane;
-      b_reg = (rhs_part[i] + rhs_part[D + i]) * rs_row.bscale;
+      const float* part = reinterpret_cast<const float*>(sm);
+#pragma unroll
+      for (int w = 0; w < TC_LOADER_WARPS - 1; ++w) b_reg += part[w * D + i];
+      b_reg *= rs_row.bscale;
     }
     tc_fence_before();
     __syncthreads();
