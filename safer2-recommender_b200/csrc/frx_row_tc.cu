@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
   uint64_t* acc_bar = bars + 4;    // [1] SYRK accumulators complete
   uint64_t* upd_bar = bars + 5;    // [1] trailing update complete
   uint64_t* col_bar = bars + 6;    // [4] columns 8q..8q+7 of the current diagonal factor are published
+  uint64_t* ld_bar = bars + 10;    // [1] the diagonal warp has read its panel rows from TMEM
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -303,6 +304,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
     mbar_init(acc_bar, 1);
     mbar_init(upd_bar, 1);
     for (int q = 0; q < 4; ++q) mbar_init(&col_bar[q], 1);
+    mbar_init(ld_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == TC_MMA_WARP) {
@@ -488,8 +490,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
       FRX_DBG_LAP(2);  // exposed wait for the trailing update
       float a[32];
       if (is_row_warp && warp >= pn) {
+        // TMEM reads run at 64 B/clk: the diagonal warp (critical path) goes first, the rows below follow
+        if (warp > pn) mbar_wait(ld_bar, (uint32_t)(pn & 1));
         uint32_t u[32];
         FRX_TMEM_LD32(u, trow + (uint32_t)c0);
+        if (warp == pn && lane == 0) mbar_arrive(ld_bar);
 #pragma unroll
         for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(u[j]);
       }
