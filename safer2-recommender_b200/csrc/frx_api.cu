@@ -257,7 +257,7 @@ extern "C" int frx_context_init_comm(frx_context* c, int rank, int world, const 
 // ---------------------------------------------------------------------------
 // Cost model of one row for the multi-GPU partition: history length + a fixed per-row share for the
 // d x d factorisation, in units of history entries.
-static const int kRowUnit = 256;
+static const int kRowUnit = 480;  // d = 256 tensor-core kernel: ~62K cycles fixed vs ~128 cycles per history entry
 
 // Contiguous row ranges balanced on sum(history length + row_unit).  Pure host code (no GPU needed).
 extern "C" int frx_partition_rows(const int* ptr, int nrows, int world, int row_unit, int* rank_begin) {
@@ -650,7 +650,11 @@ static int run_rows(frx_model* m, const RowCall& rc_) {
 static int run_rows_sharded(frx_model* m, const RowCall& rc_) {
   int rc = run_rows(m, rc_);
   if (rc) return rc;
-  if (m->ctx->world > 1 && !rc_.xmap) return allgather_rows(m->ctx, rc_.X, (size_t)m->cfg.dim, rc_.rows->rank_begin);
+  if (m->ctx->world > 1 && !rc_.xmap) {
+    m->ctx->stage_end();  // the caller's stage times the kernel; the exchange is reported separately
+    m->ctx->stage_begin("allgather_rows");
+    return allgather_rows(m->ctx, rc_.X, (size_t)m->cfg.dim, rc_.rows->rank_begin);
+  }
   return FRX_OK;
 }
 
@@ -663,7 +667,7 @@ static int stage_item_gramian(frx_model* m) {
 
 static int stage_user_loss(frx_model* m, frx_dataset* ds, const float* G, const float* pred) {
   frx_context* c = m->ctx;
-  c->stage_begin("user_loss");
+  c->stage_begin("quadform");
   LossParams p;
   memset(&p, 0, sizeof p);
   p.ptr = ds->by_user.ptr; p.col = ds->by_user.col; p.tup = ds->by_user.tup;
@@ -671,9 +675,17 @@ static int stage_user_loss(frx_model* m, frx_dataset* ds, const float* G, const 
   p.U = m->U; p.V = m->V; p.d = m->cfg.dim; p.G = G; p.pred = pred;
   p.beta = m->cfg.uobs_weight; p.halve = m->is_ials_family() ? 0 : 1;
   p.quad = m->quad; p.loss = m->loss;
-  launch_user_loss(p, m->num_users, c->stream, c->num_sms, &c->launches);
+  launch_quadform(p, ds->by_user.rank_begin[c->rank], ds->by_user.rank_begin[c->rank + 1], c->stream, &c->launches);
+  c->stage_end();
+  c->stage_begin("user_loss");
+  launch_user_loss_rows(p, c->stream, c->num_sms, &c->launches);
   CK(cudaGetLastError());
-  int rc = allgather_rows(c, m->loss, 1, ds->by_user.rank_begin);  // C4: every rank needs all losses for xi / z
+  int rc = FRX_OK;
+  if (c->world > 1) {
+    c->stage_end();
+    c->stage_begin("allgather_loss");
+    rc = allgather_rows(c, m->loss, 1, ds->by_user.rank_begin);  // C4: every rank needs all losses for xi / z
+  }
   c->stage_end();
   return rc;
 }
@@ -1015,7 +1027,7 @@ extern "C" int frx_model_compute_stats(frx_model* m, frx_dataset* ds, double* ou
   p.order = ds->by_user.order; p.num_rows = ds->by_user.num_order;
   p.U = m->U; p.V = m->V; p.d = d; p.G = m->G; p.beta = 0.f; p.halve = 0;
   p.quad = m->quad; p.loss = tmp_loss; p.obs_sq = obs;
-  launch_user_loss(p, nu, c->stream, c->num_sms, &c->launches);
+  launch_user_loss(p, 0, nu, c->stream, c->num_sms, &c->launches);
   std::vector<double> h_obs(nu);
   std::vector<float> hU((size_t)nu * d), hV((size_t)ni * d), h_ireg(ni), h_loss(nu), GU((size_t)d * d), GV((size_t)d * d);
   CK(cudaMemcpyAsync(h_obs.data(), obs, sizeof(double) * nu, cudaMemcpyDeviceToHost, c->stream));

@@ -88,7 +88,9 @@ struct LossParams {
   float* loss;          // [num_users] out (rows without history untouched)
   double* obs_sq;       // optional [num_users]: sum (pred-1)^2 in double (stats)
 };
-void launch_user_loss(const LossParams& p, int num_users, cudaStream_t s, int num_sms,
+void launch_quadform(const LossParams& p, int user_begin, int user_end, cudaStream_t s, long long* launches);
+void launch_user_loss_rows(const LossParams& p, cudaStream_t s, int num_sms, long long* launches);
+void launch_user_loss(const LossParams& p, int user_begin, int user_end, cudaStream_t s, int num_sms,
                       long long* launches);
 
 // pred[t] = v_i . u for every tuple (PredictDataset ialspp.h:469-517).

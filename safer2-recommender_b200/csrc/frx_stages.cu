@@ -567,14 +567,24 @@ void launch_gramian(const float* E, int n, int d, int cs, int bd, int fs, int fd
   if (launches) *launches += 2;
 }
 
-void launch_user_loss(const LossParams& p, int num_users, cudaStream_t s, int num_sms, long long* launches) {
+void launch_quadform(const LossParams& p, int user_begin, int user_end, cudaStream_t s, long long* launches) {
   const int d = p.d, dp = (d + 3) & ~3;
-  {
+  if (user_end > user_begin) {  // u^T G u for the users [user_begin, user_end) the loss kernel will visit
+    const int nu = user_end - user_begin;
     const size_t smem = sizeof(float) * (size_t)(QU * dp + QU * 8);
     cudaFuncSetAttribute(quadform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    quadform_kernel<<<(num_users + QU - 1) / QU, 256, smem, s>>>(p.U, num_users, d, p.G, p.quad);
+    quadform_kernel<<<(nu + QU - 1) / QU, 256, smem, s>>>(p.U + (size_t)user_begin * d, nu, d, p.G, p.quad + user_begin);
     if (launches) ++*launches;
   }
+}
+
+void launch_user_loss(const LossParams& p, int user_begin, int user_end, cudaStream_t s, int num_sms, long long* launches) {
+  launch_quadform(p, user_begin, user_end, s, launches);
+  launch_user_loss_rows(p, s, num_sms, launches);
+}
+
+void launch_user_loss_rows(const LossParams& p, cudaStream_t s, int num_sms, long long* launches) {
+  const int d = p.d, dp = (d + 3) & ~3;
   if (p.num_rows > 0) {
     const size_t smem = sizeof(float) * (size_t)(8 * dp);
     int grid = (p.num_rows + 7) / 8;
