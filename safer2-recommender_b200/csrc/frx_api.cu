@@ -108,6 +108,12 @@ struct Csr {
   int distinct = 0;
   std::vector<int> h_ptr;
   std::vector<int> rank_begin;  // row-id range per rank [world+1]
+  // long rows of this rank cut into pieces for the tensor-core row kernel (RowParams::piece_*)
+  int num_pieces = 0;
+  int num_long = 0;  // the first num_long entries of `order` are the rows cut into pieces
+  int* piece_row = nullptr;
+  int* piece_off = nullptr;
+  int* row_piece0 = nullptr;
 };
 
 struct frx_dataset {
@@ -294,6 +300,24 @@ static int finish_csr(frx_context* c, Csr& m, const int* cost_other_dim) {
   CK(cudaMalloc(&m.order, sizeof(int) * (size_t)std::max(1, m.num_order)));
   if (m.num_order)
     CK(cudaMemcpy(m.order, order.data(), sizeof(int) * (size_t)m.num_order, cudaMemcpyHostToDevice));
+  // pieces of the long rows (a popular item of ML-20M has ~70K entries: one CTA would need milliseconds)
+  std::vector<int> prow, poff, p0(std::max(1, m.nrows), -1);
+  for (int r : order) {
+    const int n = m.h_ptr[r + 1] - m.h_ptr[r];
+    if (n <= FRX_SPLIT_MIN) break;  // longest first
+    ++m.num_long;
+    p0[r] = (int)prow.size();
+    for (int off = 0; off < n; off += FRX_PIECE) { prow.push_back(r); poff.push_back(off); }
+  }
+  m.num_pieces = (int)prow.size();
+  if (m.num_pieces) {
+    CK(cudaMalloc(&m.piece_row, sizeof(int) * prow.size()));
+    CK(cudaMalloc(&m.piece_off, sizeof(int) * poff.size()));
+    CK(cudaMalloc(&m.row_piece0, sizeof(int) * p0.size()));
+    CK(cudaMemcpy(m.piece_row, prow.data(), sizeof(int) * prow.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(m.piece_off, poff.data(), sizeof(int) * poff.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(m.row_piece0, p0.data(), sizeof(int) * p0.size(), cudaMemcpyHostToDevice));
+  }
   return FRX_OK;
 }
 
@@ -341,6 +365,7 @@ extern "C" void frx_dataset_destroy(frx_dataset* d) {
   cudaStreamSynchronize(d->ctx->stream);
   for (Csr* m : {&d->by_user, &d->by_item}) {
     cudaFree(m->ptr); cudaFree(m->col); cudaFree(m->tup); cudaFree(m->order);
+    cudaFree(m->piece_row); cudaFree(m->piece_off); cudaFree(m->row_piece0);
   }
   cudaFree(d->xmap);
   cudaFree(d->user_ids_dev);
@@ -616,6 +641,28 @@ static int run_rows(frx_model* m, const RowCall& rc_) {
       CK(cudaMalloc(&dbg, 16 * sizeof(unsigned long long)));
       CK(cudaMemsetAsync(dbg, 0, 16 * sizeof(unsigned long long), c->stream));
       p.dbg = dbg;
+    }
+    static const bool no_split = getenv("FRX_NO_SPLIT") != nullptr;
+    if (rc_.rows->num_pieces > 0 && !no_split) {
+      // first launch: partial sums of the pieces of the long rows
+      p.piece_stride = row_solve_tc_piece_floats(p.d);
+      int r = c->ensure_row_scratch(p.piece_stride * (size_t)rc_.rows->num_pieces);
+      if (r) return r;
+      p.piece_scratch = c->row_scratch;
+      p.piece_row = rc_.rows->piece_row; p.piece_off = rc_.rows->piece_off; p.row_piece0 = rc_.rows->row_piece0;
+      p.num_pieces = rc_.rows->num_pieces;
+      p.piece_mode = 1;
+      launch_row_solve_tc(p, c->stream, c->num_sms, &c->launches);
+      CK(cudaGetLastError());
+      // second launch: the long rows, each started from the sum of its pieces
+      p.piece_mode = 2;
+      p.num_rows = rc_.rows->num_long;
+      launch_row_solve_tc(p, c->stream, c->num_sms, &c->launches);
+      CK(cudaGetLastError());
+      // the ordinary rows follow
+      p.piece_mode = 0;
+      p.order = rc_.rows->order + rc_.rows->num_long;
+      p.num_rows = rc_.rows->num_order - rc_.rows->num_long;
     }
     launch_row_solve_tc(p, c->stream, c->num_sms, &c->launches);
     CK(cudaGetLastError());

@@ -49,7 +49,21 @@ struct RowParams {
   int use_smem_matrix;
   int* status;  // set non-zero on a non-positive pivot
   unsigned long long* dbg;  // optional per-phase cycle counters (FRX_TC_DEBUG), else null
+  // Long rows (tensor-core path): a row with more than FRX_SPLIT_MIN entries is cut into pieces of
+  // FRX_PIECE entries whose partial SYRK sums are produced by a first launch (piece_mode = 1, one
+  // work item per piece) into piece_scratch; the main launch then starts such a row from the sum of
+  // its pieces instead of gathering it, so that no single CTA serialises a 80K-entry history.
+  const int* piece_row;    // [num_pieces] row id
+  const int* piece_off;    // [num_pieces] first entry of the piece within the row
+  const int* row_piece0;   // [rows] first piece of the row, or -1 (null when nothing is split)
+  int num_pieces;
+  int piece_mode;
+  float* piece_scratch;    // [num_pieces][piece_stride]: lower 32x32 chunks (row-major), then the rhs partial
+  size_t piece_stride;
 };
+constexpr int FRX_SPLIT_MIN = 8192;
+constexpr int FRX_PIECE = 4096;
+size_t row_solve_tc_piece_floats(int d);  // piece_stride for dimension d
 
 void launch_row_solve_generic(const RowParams& p, cudaStream_t s, int num_sms, long long* launches);
 size_t row_solve_generic_scratch_floats(int bd);  // per-CTA scratch (0 if shared memory suffices)

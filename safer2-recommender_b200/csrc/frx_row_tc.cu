@@ -222,13 +222,33 @@ __device__ __forceinline__ RowScalars row_scalars(const RowParams& p, int r, int
 // TMEM <- alpha*G + beta*I on the lower-triangle 32x32 chunks of the d x d accumulator.  Run by the
 // `nshare` warps that share TMEM lane quarter `rq` (share id `sid`); `gbuf` is a private 4 KB buffer:
 // G rows arrive as coalesced 128 B segments, are stored XOR-swizzled and read back row-per-lane.
+// Index of the lower-triangle chunk (M block rb, lane quarter rq, column chunk ch) in a piece dump.
+__device__ __forceinline__ int piece_chunk_index(int rb, int rq, int ch) {
+  return rb == 0 ? rq * (rq + 1) / 2 + ch : 10 + 5 * rq + rq * (rq - 1) / 2 + ch;
+}
+
+// With `pieces` != null the partial SYRK sums of a long row (npieces dumps of `pstride` floats, see the
+// piece mode of the kernel) are added in piece order; alpha == beta == 0 and G == null just clears.
 template <int D>
 __device__ __forceinline__ void tmem_init_system(const float* __restrict__ G, float alpha, float beta, uint32_t tmem_base,
-                                                 int rq, int sid, int nshare, float* gbuf, int lane) {
+                                                 int rq, int sid, int nshare, float* gbuf, int lane,
+                                                 const float* __restrict__ pieces = nullptr, int npieces = 0,
+                                                 size_t pstride = 0) {
   constexpr int NB = D / 128;
   const int per_rb0 = rq + 1;                       // chunks with j <= i for M block 0
   const int total = NB == 2 ? 2 * rq + 6 : rq + 1;  // (rq + 1) + (4 + rq + 1)
   float4 gv[8];
+  if (G == nullptr) {  // clear only
+    uint32_t z[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) z[j] = 0u;
+    for (int c = sid; c < total; c += nshare) {
+      const int rb = c < per_rb0 ? 0 : 1, ch = c < per_rb0 ? c : c - per_rb0;
+      FRX_TMEM_ST32(tmem_base + ((uint32_t)(32 * rq) << 16) + (rb ? 256u : 0u) + (uint32_t)(32 * ch), z);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    return;
+  }
   auto fetch = [&](int c) {
     const int rb = c < per_rb0 ? 0 : 1, ch = c < per_rb0 ? c : c - per_rb0;
     const float* gblk = G + (size_t)(128 * rb + 32 * rq) * D + 32 * ch;
@@ -259,14 +279,29 @@ __device__ __forceinline__ void tmem_init_system(const float* __restrict__ G, fl
         u[4 * c4 + t4] = __float_as_uint(m);
       }
     }
+    for (int pc = 0; pc < npieces; ++pc) {  // lane = chunk row: 128 contiguous bytes per lane
+      const float4* src = reinterpret_cast<const float4*>(pieces + (size_t)pc * pstride +
+                                                          (size_t)piece_chunk_index(rb, rq, ch) * 1024 + lane * 32);
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 s4 = __ldcs(src + c4);
+        u[4 * c4 + 0] = __float_as_uint(__uint_as_float(u[4 * c4 + 0]) + s4.x);
+        u[4 * c4 + 1] = __float_as_uint(__uint_as_float(u[4 * c4 + 1]) + s4.y);
+        u[4 * c4 + 2] = __float_as_uint(__uint_as_float(u[4 * c4 + 2]) + s4.z);
+        u[4 * c4 + 3] = __float_as_uint(__uint_as_float(u[4 * c4 + 3]) + s4.w);
+      }
+    }
     FRX_TMEM_ST32(tmem_base + ((uint32_t)(32 * rq) << 16) + (rb ? 256u : 0u) + (uint32_t)(32 * ch), u);
   }
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-template <int D>
+// MODE 0: ordinary rows.  MODE 1: the piece launch (phase A only, partial sums dumped to
+// RowParams::piece_scratch).  MODE 2: long rows, started from the sum of their pieces (no gather).
+template <int D, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p) {
   using L = TcLayout<D>;
+  constexpr bool PIECE = MODE == 1, LONG = MODE == 2;
   constexpr int P = L::P;
   constexpr int F4 = D / 32;   // float4 loads per loader lane
   constexpr int C = 4 * F4;    // floats per loader lane
@@ -323,10 +358,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
   // alpha*G + beta*I of the first row; for the later rows the warps that are idle during the back
   // substitution of the previous row do it (TMEM is free again by then)
   float* gbuf = reinterpret_cast<float*>(sm + L::kGbufOff) + warp * 1024;
-  if ((int)blockIdx.x < p.num_rows) {
-    const int r0 = p.order[blockIdx.x];
-    const RowScalars s0 = row_scalars(p, r0, p.ptr[r0 + 1] - p.ptr[r0]);
-    tmem_init_system<D>(p.G, s0.alpha, s0.beta, tmem_base, warp & 3, warp >> 2, 4, gbuf, lane);
+  const int num_work = PIECE ? p.num_pieces : p.num_rows;
+  if ((int)blockIdx.x < num_work) {
+    if (PIECE) {
+      tmem_init_system<D>(nullptr, 0.f, 0.f, tmem_base, warp & 3, warp >> 2, 4, gbuf, lane);
+    } else {
+      const int r0 = p.order[blockIdx.x];
+      const RowScalars s0 = row_scalars(p, r0, p.ptr[r0 + 1] - p.ptr[r0]);
+      if (LONG) {
+        const int n0 = p.ptr[r0 + 1] - p.ptr[r0];
+        tmem_init_system<D>(p.G, s0.alpha, s0.beta, tmem_base, warp & 3, warp >> 2, 4, gbuf, lane,
+                            p.piece_scratch + (size_t)p.row_piece0[r0] * p.piece_stride,
+                            (n0 + FRX_PIECE - 1) / FRX_PIECE, p.piece_stride);
+      } else {
+        tmem_init_system<D>(p.G, s0.alpha, s0.beta, tmem_base, warp & 3, warp >> 2, 4, gbuf, lane);
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -339,12 +386,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
   long long tstamp = clock64();
 #define FRX_DBG_LAP(slot) do { if (p.dbg && warp == P - 1 && lane == 0) { const long long now_ = clock64(); dbg_acc[slot] += (unsigned long long)(now_ - tstamp); tstamp = now_; } } while (0)
 
-  for (int ri = blockIdx.x; ri < p.num_rows; ri += gridDim.x, ++row_count) {
-    const int r = p.order[ri];
+  for (int ri = blockIdx.x; ri < num_work; ri += gridDim.x, ++row_count) {
+    // A work item is a row, or (piece mode) one FRX_PIECE-entry piece of a long row.
+    const int r = PIECE ? p.piece_row[ri] : p.order[ri];
     const int beg = p.ptr[r];
     const int n = p.ptr[r + 1] - beg;
     const int xr = p.xmap ? p.xmap[r] : r;
-    const int T = (n + KT - 1) / KT;
+    const int e0 = PIECE ? p.piece_off[ri] : 0;             // first entry gathered here
+    const int pc_row = LONG ? p.row_piece0[r] : -1;         // first piece of a pre-summed long row
+    const int n_here = PIECE ? min(FRX_PIECE, n - e0) : (LONG ? 0 : n);
+    const int T = (n_here + KT - 1) / KT;
     int dup_lo = 0, dup_hi = 0;
     if (item_side && n > 128 && (n & 127) != 0) {  // stale tail, safer2.h:200-204 (B-1)
       const int kf = n >> 7;
@@ -366,8 +417,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
       for (int u = warp; u < SL * T; u += TC_LOADER_WARPS - 1) {
         const int t = u / SL, w8 = u % SL;
         const int slab = w8 * C;  // first feature of this unit
-        const int e = t * KT + lane;
-        const bool valid = e < n;
+        const int e = e0 + t * KT + lane;  // entry index within the row
+        const bool valid = e < e0 + n_here;
         float4 v[F4];
         float sq = 0.f, qr = 0.f;
         if (valid) {
@@ -448,6 +499,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
         }
         __syncwarp();
       }
+      if (T == 0 && lane == 0) mbar_arrive(acc_bar);  // pre-summed row: nothing to accumulate
     }
     tile_base += (uint32_t)T;
 
@@ -472,7 +524,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
       const float* part = reinterpret_cast<const float*>(sm);
 #pragma unroll
       for (int w = 0; w < TC_LOADER_WARPS - 1; ++w) b_reg += part[w * D + i];
-      b_reg *= rs_row.bscale;
+      if (LONG) {
+        const int npc = (n + FRX_PIECE - 1) / FRX_PIECE;
+        for (int pc = 0; pc < npc; ++pc)
+          b_reg += p.piece_scratch[(size_t)(pc_row + pc) * p.piece_stride + (p.piece_stride - D) + i];
+      }
+      if (!PIECE) b_reg *= rs_row.bscale;
+    }
+    if (PIECE) {
+      // ---- piece mode: dump the partial sums (lower chunks + rhs) and clear TMEM for the next piece ----
+      float* dst = p.piece_scratch + (size_t)ri * p.piece_stride;
+      if (is_row_warp) dst[(p.piece_stride - D) + 32 * warp + lane] = b_reg;
+      {
+        const int rq_ = warp & 3, sid = warp >> 2;
+        const int per_rb0 = rq_ + 1, total = D == 256 ? 2 * rq_ + 6 : rq_ + 1;
+        uint32_t z[32];
+        for (int c = sid; c < total; c += 4) {
+          const int rb_ = c < per_rb0 ? 0 : 1, ch = c < per_rb0 ? c : c - per_rb0;
+          const uint32_t ta = tmem_base + ((uint32_t)(32 * rq_) << 16) + (rb_ ? 256u : 0u) + (uint32_t)(32 * ch);
+          uint32_t u[32];
+          FRX_TMEM_LD32(u, ta);
+          float4* out = reinterpret_cast<float4*>(dst + (size_t)piece_chunk_index(rb_, rq_, ch) * 1024 + lane * 32);
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4)
+            __stcs(out + c4, make_float4(__uint_as_float(u[4 * c4]), __uint_as_float(u[4 * c4 + 1]),
+                                         __uint_as_float(u[4 * c4 + 2]), __uint_as_float(u[4 * c4 + 3])));
+#pragma unroll
+          for (int j = 0; j < 32; ++j) z[j] = 0u;
+          FRX_TMEM_ST32(ta, z);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      continue;
     }
     tc_fence_before();
     __syncthreads();
@@ -686,11 +772,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
       const int rin = ri + (int)gridDim.x;
       if (rin < p.num_rows) {
         const int rn = p.order[rin];
-        const RowScalars sn = row_scalars(p, rn, p.ptr[rn + 1] - p.ptr[rn]);
+        const int nn = p.ptr[rn + 1] - p.ptr[rn];
+        const RowScalars sn = row_scalars(p, rn, nn);
         constexpr int nshare = (TC_LOADER_WARPS - P) / 4;
         tc_fence_after();
-        tmem_init_system<D>(p.G, sn.alpha, sn.beta, tmem_base, warp & 3, (warp - P) >> 2, nshare,
-                            gbuf, lane);
+        if (LONG)
+          tmem_init_system<D>(p.G, sn.alpha, sn.beta, tmem_base, warp & 3, (warp - P) >> 2, nshare, gbuf, lane,
+                              p.piece_scratch + (size_t)p.row_piece0[rn] * p.piece_stride,
+                              (nn + FRX_PIECE - 1) / FRX_PIECE, p.piece_stride);
+        else
+          tmem_init_system<D>(p.G, sn.alpha, sn.beta, tmem_base, warp & 3, (warp - P) >> 2, nshare, gbuf, lane);
       }
     }
 #pragma unroll 1
@@ -747,23 +838,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
 
 }  // namespace
 
+size_t row_solve_tc_piece_floats(int d) { return (size_t)(d == 256 ? 36 : 10) * 1024 + (size_t)d; }
+
 bool row_solve_tc_supported(const RowParams& p) {
   const bool mode_ok = p.mode == RM_IALS || p.mode == RM_SAFER_U || p.mode == RM_SAFER_V;
   return mode_ok && p.cs == 0 && p.bd == p.d && (p.d == 128 || p.d == 256);
 }
 
+template <int D, int MODE>
+static void launch_tc_instance(const RowParams& p, int work, cudaStream_t s, int num_sms) {
+  const int smem = TcLayout<D>::kTotal + 1024;
+  cudaFuncSetAttribute(row_solve_tc_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int grid = num_sms < work ? num_sms : work;
+  row_solve_tc_kernel<D, MODE><<<grid, TC_THREADS, smem, s>>>(p);
+}
+
+// p.piece_mode: 0 ordinary rows (p.order / p.num_rows), 1 pieces (p.piece_* / p.num_pieces),
+// 2 pre-summed long rows (p.order / p.num_rows, every row has pieces).
 void launch_row_solve_tc(const RowParams& p, cudaStream_t s, int num_sms, long long* launches) {
-  if (p.num_rows <= 0) return;
+  const int work = p.piece_mode == 1 ? p.num_pieces : p.num_rows;
+  if (work <= 0) return;
   if (p.d == 256) {
-    const int smem = TcLayout<256>::kTotal + 1024;
-    cudaFuncSetAttribute(row_solve_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    int grid = num_sms < p.num_rows ? num_sms : p.num_rows;
-    row_solve_tc_kernel<256><<<grid, TC_THREADS, smem, s>>>(p);
+    if (p.piece_mode == 1) launch_tc_instance<256, 1>(p, work, s, num_sms);
+    else if (p.piece_mode == 2) launch_tc_instance<256, 2>(p, work, s, num_sms);
+    else launch_tc_instance<256, 0>(p, work, s, num_sms);
   } else {
-    const int smem = TcLayout<128>::kTotal + 1024;
-    cudaFuncSetAttribute(row_solve_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    int grid = num_sms < p.num_rows ? num_sms : p.num_rows;
-    row_solve_tc_kernel<128><<<grid, TC_THREADS, smem, s>>>(p);
+    if (p.piece_mode == 1) launch_tc_instance<128, 1>(p, work, s, num_sms);
+    else if (p.piece_mode == 2) launch_tc_instance<128, 2>(p, work, s, num_sms);
+    else launch_tc_instance<128, 0>(p, work, s, num_sms);
   }
   if (launches) ++*launches;
 }
