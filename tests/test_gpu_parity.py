@@ -289,6 +289,51 @@ def test_tensor_core_row_kernel_epoch(pkg, O, ctx, name, cfg, d):
     ds.close()
 
 
+@pytest.mark.parametrize("name,cfg,d,long_side", [
+    ("safer2", dict(uobs_weight=0.05, reg=0.05, bandwidth=0.15), 128, "item"),
+    ("ials", dict(uobs_weight=0.1, reg=0.05), 256, "item"),
+    ("safer2", dict(uobs_weight=0.05, reg=0.05, bandwidth=0.15), 128, "user"),
+])
+def test_tensor_core_long_rows_are_split(pkg, O, ctx, name, cfg, d, long_side):
+    """Rows with more than 8192 entries take the piece path of the tensor-core kernel (partial SYRK
+    sums of 4096-entry pieces, then a pre-summed solve).  Lengths 9000 and 8200 are split (the
+    second with an 8-entry last piece), 8192 is the longest unsplit row; the result must agree with
+    the fp32 oracle like any other row.  (A 9000-term fp32 sum carries ~1e-5 of rounding in the oracle's
+    sequential order as well, which the solve amplifies: the long rows get a looser per-row bound; a wrong
+    piece offset, a dropped piece or a missing rhs partial shows up as an O(1) error.)"""
+    rng = np.random.default_rng(77)
+    big, small = 9000, 48
+    a, b = [], []   # a: index on the big side, b: index on the small side
+    for j, n in ((0, 9000), (1, 8200), (2, 8192)):
+        a.append(np.arange(n)); b.append(np.full(n, j))
+    for i in range(big):
+        k = rng.integers(2, 6)
+        a.append(np.full(k, i)); b.append(rng.choice(np.arange(3, small), size=k, replace=False))
+    a = np.concatenate(a).astype(np.int32); b = np.concatenate(b).astype(np.int32)
+    perm = rng.permutation(len(a))
+    a, b = a[perm], b[perm]
+    if long_side == "item":
+        users, items, nu, ni = a, b, big, small
+    else:
+        users, items, nu, ni = b, a, small, big
+    ods, om, ds, m = make_pair(pkg, O, ctx, users, items, nu, ni, model=name, dim=d, **cfg)
+    om.initialize(ods)
+    m.initialize(ds)
+    om.train(ods)
+    m.train(ds)
+    U, V = m.factors()
+    Uo, Vo = om.factors()
+    X, Xo = (V, Vo) if long_side == "item" else (U, Uo)
+    Y, Yo = (U, Uo) if long_side == "item" else (V, Vo)
+    rowerr = np.linalg.norm(X - Xo, axis=1) / np.maximum(np.linalg.norm(Xo, axis=1), 1e-12)
+    print("long-row errors", rowerr[:3], "other rows max", rowerr[3:].max(), "other side", rel_fro(Y, Yo))
+    assert rowerr[:3].max() < 5e-4, rowerr[:3]
+    assert rowerr[3:].max() < 1e-4, float(rowerr[3:].max())
+    assert rel_fro(Y, Yo) < FACTOR_TOL, rel_fro(Y, Yo)
+    m.close()
+    ds.close()
+
+
 def test_multi_gpu_row_sharded_epoch():
     """2-rank NCCL run of tests/dist_parity.py (skipped on a 1-GPU box)."""
     import subprocess
