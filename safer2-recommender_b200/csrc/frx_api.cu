@@ -114,6 +114,11 @@ struct Csr {
   int* piece_row = nullptr;
   int* piece_off = nullptr;
   int* row_piece0 = nullptr;
+  // FRX_LOSS_CHUNK-entry chunks of this rank's rows for the two-pass user loss (LossParams::chunk_*)
+  int num_chunks = 0;
+  int* chunk_row = nullptr;
+  int* chunk_off = nullptr;
+  float* resid = nullptr;  // [nnz]
 };
 
 struct frx_dataset {
@@ -309,6 +314,21 @@ static int finish_csr(frx_context* c, Csr& m, const int* cost_other_dim) {
     p0[r] = (int)prow.size();
     for (int off = 0; off < n; off += FRX_PIECE) { prow.push_back(r); poff.push_back(off); }
   }
+  {
+    std::vector<int> crow, coff;
+    for (int r : order) {
+      const int n = m.h_ptr[r + 1] - m.h_ptr[r];
+      for (int off = 0; off < n; off += FRX_LOSS_CHUNK) { crow.push_back(r); coff.push_back(off); }
+    }
+    m.num_chunks = (int)crow.size();
+    if (m.num_chunks) {
+      CK(cudaMalloc(&m.chunk_row, sizeof(int) * crow.size()));
+      CK(cudaMalloc(&m.chunk_off, sizeof(int) * coff.size()));
+      CK(cudaMemcpy(m.chunk_row, crow.data(), sizeof(int) * crow.size(), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(m.chunk_off, coff.data(), sizeof(int) * coff.size(), cudaMemcpyHostToDevice));
+      CK(cudaMalloc(&m.resid, sizeof(float) * (size_t)std::max(1, m.h_ptr[m.nrows])));
+    }
+  }
   m.num_pieces = (int)prow.size();
   if (m.num_pieces) {
     CK(cudaMalloc(&m.piece_row, sizeof(int) * prow.size()));
@@ -366,6 +386,7 @@ extern "C" void frx_dataset_destroy(frx_dataset* d) {
   for (Csr* m : {&d->by_user, &d->by_item}) {
     cudaFree(m->ptr); cudaFree(m->col); cudaFree(m->tup); cudaFree(m->order);
     cudaFree(m->piece_row); cudaFree(m->piece_off); cudaFree(m->row_piece0);
+    cudaFree(m->chunk_row); cudaFree(m->chunk_off); cudaFree(m->resid);
   }
   cudaFree(d->xmap);
   cudaFree(d->user_ids_dev);
@@ -722,6 +743,8 @@ static int stage_user_loss(frx_model* m, frx_dataset* ds, const float* G, const 
   p.U = m->U; p.V = m->V; p.d = m->cfg.dim; p.G = G; p.pred = pred;
   p.beta = m->cfg.uobs_weight; p.halve = m->is_ials_family() ? 0 : 1;
   p.quad = m->quad; p.loss = m->loss;
+  p.resid = ds->by_user.resid; p.chunk_row = ds->by_user.chunk_row; p.chunk_off = ds->by_user.chunk_off;
+  p.num_chunks = ds->by_user.num_chunks;
   launch_quadform(p, ds->by_user.rank_begin[c->rank], ds->by_user.rank_begin[c->rank + 1], c->stream, &c->launches);
   c->stage_end();
   c->stage_begin("user_loss");
@@ -1074,6 +1097,8 @@ extern "C" int frx_model_compute_stats(frx_model* m, frx_dataset* ds, double* ou
   p.order = ds->by_user.order; p.num_rows = ds->by_user.num_order;
   p.U = m->U; p.V = m->V; p.d = d; p.G = m->G; p.beta = 0.f; p.halve = 0;
   p.quad = m->quad; p.loss = tmp_loss; p.obs_sq = obs;
+  p.resid = ds->by_user.resid; p.chunk_row = ds->by_user.chunk_row; p.chunk_off = ds->by_user.chunk_off;
+  p.num_chunks = ds->by_user.num_chunks;
   launch_user_loss(p, 0, nu, c->stream, c->num_sms, &c->launches);
   std::vector<double> h_obs(nu);
   std::vector<float> hU((size_t)nu * d), hV((size_t)ni * d), h_ireg(ni), h_loss(nu), GU((size_t)d * d), GV((size_t)d * d);

@@ -101,7 +101,16 @@ struct LossParams {
   float* quad;          // [num_users] scratch: u^T G u
   float* loss;          // [num_users] out (rows without history untouched)
   double* obs_sq;       // optional [num_users]: sum (pred-1)^2 in double (stats)
+  // Two-pass form (used when resid != null and pred == null): pass 1 writes the residual of every
+  // history entry, one warp per FRX_LOSS_CHUNK-entry chunk (chunk_row / chunk_off), so that a 6K-entry
+  // history is spread over many warps; pass 2 adds them per user in history order exactly like the
+  // reference's running float sum.
+  float* resid;          // [nnz] scratch, indexed like col
+  const int* chunk_row;
+  const int* chunk_off;
+  int num_chunks;
 };
+constexpr int FRX_LOSS_CHUNK = 256;
 void launch_quadform(const LossParams& p, int user_begin, int user_end, cudaStream_t s, long long* launches);
 void launch_user_loss_rows(const LossParams& p, cudaStream_t s, int num_sms, long long* launches);
 void launch_user_loss(const LossParams& p, int user_begin, int user_end, cudaStream_t s, int num_sms,

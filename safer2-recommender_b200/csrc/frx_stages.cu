@@ -313,6 +313,80 @@ __global__ void __launch_bounds__(256) user_loss_kernel(LossParams p) {
   }
 }
 
+// Pass 1 of the two-pass user loss: resid[beg + e] = u . v_{col[beg+e]} - 1 for the entries of one chunk.
+__global__ void __launch_bounds__(256) user_resid_kernel(LossParams p) {
+  extern __shared__ __align__(16) float sh[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int d = p.d;
+  float* us = sh + warp * ((d + 3) & ~3);
+  for (int it = blockIdx.x * 8 + warp; it < p.num_chunks; it += gridDim.x * 8) {
+    const int u = p.chunk_row[it], off = p.chunk_off[it];
+    const int beg = p.ptr[u] + off;
+    const int n = min(FRX_LOSS_CHUNK, p.ptr[u + 1] - beg);
+    __syncwarp();
+    for (int k = lane; k < d; k += 32) us[k] = p.U[(size_t)u * d + k];
+    __syncwarp();
+    int e = 0;
+    if ((d & 127) == 0) {
+      for (; e + 8 <= n; e += 8) {
+        const float* vp[8];
+        float acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          vp[q] = p.V + (size_t)__ldg(p.col + beg + e + q) * d;
+          acc[q] = 0.f;
+        }
+        for (int k = lane * 4; k < d; k += 128) {
+          const float4 u4 = *reinterpret_cast<const float4*>(us + k);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 v4 = __ldg(reinterpret_cast<const float4*>(vp[q] + k));
+            acc[q] = fmaf(v4.x, u4.x, acc[q]);
+            acc[q] = fmaf(v4.y, u4.y, acc[q]);
+            acc[q] = fmaf(v4.z, u4.z, acc[q]);
+            acc[q] = fmaf(v4.w, u4.w, acc[q]);
+          }
+        }
+        float mine = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float r = warp_sum(acc[q]) - 1.f;
+          if (lane == q) mine = r;
+        }
+        if (lane < 8) p.resid[beg + e + lane] = mine;
+      }
+    }
+    for (; e < n; ++e) {
+      const float* v0 = p.V + (size_t)p.col[beg + e] * d;
+      float a0 = 0.f;
+      for (int k = lane; k < d; k += 32) a0 = fmaf(__ldg(v0 + k), us[k], a0);
+      a0 = warp_sum(a0);
+      if (lane == 0) p.resid[beg + e] = a0 - 1.f;
+    }
+  }
+}
+
+// Pass 2: per user, the running float sum of the squared residuals in history order (safer2.h:86-99).
+__global__ void __launch_bounds__(128) user_loss_finish_kernel(LossParams p) {
+  const int ri = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ri >= p.num_rows) return;
+  const int u = p.order[ri];
+  const int beg = p.ptr[u], n = p.ptr[u + 1] - beg;
+  float loss = 0.f;
+  double obs = 0.0;
+  const float* r = p.resid + beg;
+  for (int e = 0; e < n; ++e) {
+    const double s0 = (double)r[e];
+    loss = (float)((double)loss + s0 * s0);
+    obs += s0 * s0;
+  }
+  loss /= (float)n;
+  loss += p.beta * p.quad[u];
+  if (p.halve) loss *= 0.5f;
+  p.loss[u] = loss;
+  if (p.obs_sq) p.obs_sq[u] = obs;
+}
+
 __global__ void __launch_bounds__(256) predict_kernel(const int* __restrict__ ptr, const int* __restrict__ col,
                                                       const int* __restrict__ tup, const int* __restrict__ order,
                                                       int num_rows, const float* __restrict__ U,
@@ -585,6 +659,17 @@ void launch_user_loss(const LossParams& p, int user_begin, int user_end, cudaStr
 
 void launch_user_loss_rows(const LossParams& p, cudaStream_t s, int num_sms, long long* launches) {
   const int d = p.d, dp = (d + 3) & ~3;
+  if (p.num_rows > 0 && p.resid && !p.pred && p.num_chunks > 0) {
+    const size_t smem = sizeof(float) * (size_t)(8 * dp);
+    int grid = (p.num_chunks + 7) / 8;
+    const int cap = num_sms * 8;
+    if (grid > cap) grid = cap;
+    cudaFuncSetAttribute(user_resid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    user_resid_kernel<<<grid, 256, smem, s>>>(p);
+    user_loss_finish_kernel<<<(p.num_rows + 127) / 128, 128, 0, s>>>(p);
+    if (launches) *launches += 2;
+    return;
+  }
   if (p.num_rows > 0) {
     const size_t smem = sizeof(float) * (size_t)(8 * dp);
     int grid = (p.num_rows + 7) / 8;
