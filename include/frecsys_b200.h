@@ -107,6 +107,14 @@ int frx_model_get_factors(frx_model* m, float* U, float* V);
  * buffers must stay valid until frx_context_sync; use pinned memory).  This is the
  * per-epoch host->device leg of a caller that keeps its factors in host memory. */
 int frx_model_upload_factors(frx_model* m, const float* U, const float* V);
+/* Row-sharded variants for a multi-rank job (one process per GPU) whose factors live in host memory:
+ * each rank copies only the rows it owns under frx_partition_rows over `train` (by user for U, by item
+ * for V); after the upload the blocks are all-gathered over NCCL so every rank holds the full factors,
+ * after the download the caller's host array holds this rank's rows (other rows untouched).  With one
+ * rank they equal the calls above.  The reference keeps U, V in one process' memory (recommender.h);
+ * this is the per-process view of that array. */
+int frx_model_upload_factors_sharded(frx_model* m, frx_dataset* train, const float* U, const float* V);
+int frx_model_get_factors_sharded(frx_model* m, frx_dataset* train, float* U, float* V);
 /* Initialize(const Dataset&) — safer2.h:819-838, safer2pp.h, erm_mf.h:573-587,
  * cvar_mf.h:710-726; a no-op for iALS / iALS++ (run_model.cc:246-257). */
 int frx_model_initialize(frx_model* m, frx_dataset* train);

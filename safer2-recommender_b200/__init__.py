@@ -19,7 +19,7 @@ MODEL_IDS = {"ials": 0, "ialspp": 1, "erm_mf": 2, "cvar_mf": 3, "safer2": 4, "sa
 
 EXPORTS = [
     "frx_last_error", "frx_context_create", "frx_context_destroy", "frx_context_sync",
-    "frx_context_stream", "frx_comm_unique_id", "frx_context_init_comm", "frx_partition_rows", "frx_dataset_create",
+    "frx_context_stream", "frx_comm_unique_id", "frx_context_init_comm", "frx_partition_rows", "frx_dataset_create", "frx_model_upload_factors_sharded", "frx_model_get_factors_sharded",
     "frx_dataset_destroy", "frx_dataset_info", "frx_dataset_get_csr", "frx_model_create",
     "frx_model_destroy", "frx_model_init_factors", "frx_model_set_factors", "frx_model_get_factors", "frx_model_upload_factors",
     "frx_model_initialize", "frx_model_train", "frx_model_stage", "frx_model_get_state",
@@ -104,6 +104,8 @@ def lib():
     L.frx_model_set_factors.argtypes = [vp, fp, fp]
     L.frx_model_get_factors.argtypes = [vp, fp, fp]
     L.frx_model_upload_factors.argtypes = [vp, fp, fp]
+    L.frx_model_upload_factors_sharded.argtypes = [vp, vp, fp, fp]
+    L.frx_model_get_factors_sharded.argtypes = [vp, vp, fp, fp]
     L.frx_model_initialize.argtypes = [vp, vp]
     L.frx_model_train.argtypes = [vp, vp]
     L.frx_model_stage.argtypes = [vp, vp, C.c_int]
@@ -251,6 +253,15 @@ class Model:
         """Overwrite factors only (state untouched), asynchronously; U, V must stay alive
         (ideally pinned) until the context is synchronised."""
         _check(lib().frx_model_upload_factors(self.h, _fp(U), _fp(V)))
+
+    def upload_factors_sharded(self, ds, U, V):
+        """Multi-rank H2D leg: this rank uploads only the rows it owns, then the blocks are all-gathered."""
+        _check(lib().frx_model_upload_factors_sharded(self.h, ds.h, _fp(U), _fp(V)))
+
+    def factors_sharded(self, ds, U, V):
+        """Multi-rank D2H leg: only this rank's rows of U and V are written into the host arrays."""
+        _check(lib().frx_model_get_factors_sharded(self.h, ds.h, _fp(U), _fp(V)))
+        return U, V
 
     def factors(self, U=None, V=None):
         U = np.zeros((self.num_users, self.dim), np.float32) if U is None else U

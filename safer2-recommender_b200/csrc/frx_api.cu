@@ -614,6 +614,50 @@ extern "C" int frx_model_get_factors(frx_model* m, float* U, float* V) {
   return frx_context_sync(c);
 }
 
+// Row-sharded host<->device legs for a multi-rank job whose factors live in host memory: every rank
+// moves only the rows it owns (the ranges of frx_partition_rows over `train`), the rest travels over
+// NVLink.  With one rank these are frx_model_upload_factors / frx_model_get_factors.
+extern "C" int frx_model_upload_factors_sharded(frx_model* m, frx_dataset* train, const float* U, const float* V) {
+  frx_context* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  if (c->world <= 1) return frx_model_upload_factors(m, U, V);
+  const size_t d = m->cfg.dim;
+  const Csr* side[2] = {&train->by_user, &train->by_item};
+  const float* host[2] = {U, V};
+  float* dev[2] = {m->U, m->V};
+  for (int k = 0; k < 2; ++k) {
+    if (!host[k]) continue;
+    const size_t b = side[k]->rank_begin[c->rank], e = side[k]->rank_begin[c->rank + 1];
+    if (e > b)
+      CK(cudaMemcpyAsync(dev[k] + b * d, host[k] + b * d, sizeof(float) * (e - b) * d, cudaMemcpyHostToDevice, c->stream));
+    // rows past the last id that occurs in `train` belong to no rank: every rank takes them from the host
+    const size_t last = side[k]->nrows, total = k == 0 ? m->num_users : m->num_items;
+    if (total > last)
+      CK(cudaMemcpyAsync(dev[k] + last * d, host[k] + last * d, sizeof(float) * (total - last) * d, cudaMemcpyHostToDevice, c->stream));
+    { const int rc_ = allgather_rows(c, dev[k], d, side[k]->rank_begin); if (rc_) return rc_; }
+  }
+  return FRX_OK;
+}
+
+extern "C" int frx_model_get_factors_sharded(frx_model* m, frx_dataset* train, float* U, float* V) {
+  frx_context* c = m->ctx;
+  if (c->world <= 1) return frx_model_get_factors(m, U, V);
+  const size_t d = m->cfg.dim;
+  const Csr* side[2] = {&train->by_user, &train->by_item};
+  float* host[2] = {U, V};
+  const float* dev[2] = {m->U, m->V};
+  for (int k = 0; k < 2; ++k) {
+    if (!host[k]) continue;
+    const size_t b = side[k]->rank_begin[c->rank], e = side[k]->rank_begin[c->rank + 1];
+    if (e > b)
+      CK(cudaMemcpyAsync(host[k] + b * d, dev[k] + b * d, sizeof(float) * (e - b) * d, cudaMemcpyDeviceToHost, c->stream));
+    const size_t last = side[k]->nrows, total = k == 0 ? m->num_users : m->num_items;
+    if (total > last && c->rank == c->world - 1)  // the unowned tail goes with the last rank
+      CK(cudaMemcpyAsync(host[k] + last * d, dev[k] + last * d, sizeof(float) * (total - last) * d, cudaMemcpyDeviceToHost, c->stream));
+  }
+  return frx_context_sync(c);
+}
+
 static int ensure_pred(frx_model* m, size_t n) {
   if (n <= m->pred_cap) return FRX_OK;
   if (m->pred) cudaFree(m->pred);

@@ -69,6 +69,24 @@ def main():
         if not same:
             print(f"[dist_parity] rank {rank}: replicated state differs from rank 0 for {name} d={d}", flush=True)
             failures += 1
+        # row-sharded host legs: upload own rows + all-gather == full upload; download writes own rows only
+        rngs = np.random.default_rng(5)
+        Uh = rngs.standard_normal((nu, d)).astype(np.float32)
+        Vh = rngs.standard_normal((ni, d)).astype(np.float32)
+        m.upload_factors_sharded(ds, Uh, Vh)
+        ctx.sync()
+        U2, V2 = m.factors()
+        ub = pkg.partition_rows(ds.csr(0, ds.max_user + 1)[0], world)
+        ib = pkg.partition_rows(ds.csr(1, ds.max_item + 1)[0], world)
+        Ud = np.full((nu, d), -7.0, np.float32)
+        Vd = np.full((ni, d), -7.0, np.float32)
+        m.factors_sharded(ds, Ud, Vd)
+        own_ok = (np.array_equal(Ud[ub[rank]:ub[rank + 1]], Uh[ub[rank]:ub[rank + 1]]) and
+                  np.array_equal(Vd[ib[rank]:ib[rank + 1]], Vh[ib[rank]:ib[rank + 1]]) and
+                  np.all(Ud[:ub[rank]] == -7.0) and np.all(Ud[ub[rank + 1]:ds.max_user + 1] == -7.0))
+        if not (np.array_equal(U2, Uh) and np.array_equal(V2, Vh) and own_ok):
+            print(f"[dist_parity] rank {rank}: sharded factor transfer mismatch for {name} d={d}", flush=True)
+            failures += 1
         m.close()
         ds.close()
     f = torch.tensor([failures], device="cuda")
