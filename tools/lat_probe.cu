@@ -12,7 +12,7 @@ __global__ void probe(float seed, long long* out, float* sink) {
   // SHFL chain
   t0 = clock64();
 #pragma unroll 16
-  for (int i = 0; i < N; ++i) x = __shfl_sync(0xffffffffu, x, (i + 1) & 31);
+  for (int i = 0; i < N; ++i) x = __shfl_sync(0xffffffffu, x, (lane + 1 + (i & 1)) & 31) + 1e-6f;  // rotation: result stays lane-dependent
   t1 = clock64(); if (lane == 0) out[0] = t1 - t0;
   // MUFU.RSQ chain
   t0 = clock64();
@@ -27,7 +27,7 @@ __global__ void probe(float seed, long long* out, float* sink) {
   // SHFL + RSQ + FMUL (the pivot chain)
   t0 = clock64();
 #pragma unroll 16
-  for (int i = 0; i < N; ++i) { float p = __shfl_sync(0xffffffffu, x, (i + 1) & 31); x = x * rsq(p) + 1.f; }
+  for (int i = 0; i < N; ++i) { float p = __shfl_sync(0xffffffffu, x, (lane + 1) & 31); x = x * rsq(p) + 1.f + lane * 1e-3f; }
   t1 = clock64(); if (lane == 0) out[3] = t1 - t0;
   // STS -> syncwarp -> LDS round trip
   t0 = clock64();
@@ -42,7 +42,7 @@ __global__ void probe(float seed, long long* out, float* sink) {
 #pragma unroll 4
   for (int i = 0; i < N / 16; ++i) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __shfl_sync(0xffffffffu, v[j], (i + j) & 31);
+    for (int j = 0; j < 16; ++j) v[j] = __shfl_sync(0xffffffffu, v[j], (lane + j + 1) & 31);
   }
   t1 = clock64(); if (lane == 0) out[5] = t1 - t0;
 #pragma unroll
@@ -77,7 +77,7 @@ int main() {
   probe<<<1, 32>>>(1.5f, d, s); probe<<<1, 32>>>(1.5f, d, s);
   if (cudaDeviceSynchronize() != cudaSuccess) { printf("failed\n"); return 1; }
   long long h[8]; cudaMemcpy(h, d, 64, cudaMemcpyDeviceToHost);
-  const char* names[8] = {"SHFL.IDX dependent", "MUFU.RSQ dependent", "FFMA dependent", "SHFL+RSQ+FFMA chain", "STS->LDS round trip (2 syncwarp)",
+  const char* names[8] = {"SHFL.IDX + FADD dependent", "MUFU.RSQ dependent", "FFMA dependent", "SHFL+RSQ+FFMA chain", "STS->LDS round trip (2 syncwarp)",
                           "SHFL independent (per instr)", "FFMA 3-reg independent (per instr)", "FFMA2 independent (per instr)"};
   const double div[8] = {N, N, N, N, N, N, N, N / 2.0};
   for (int i = 0; i < 8; ++i) printf("%-40s %.1f cycles\n", names[i], h[i] / div[i]);
