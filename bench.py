@@ -174,7 +174,7 @@ def main():
     ap.add_argument("--shape", default="ml20m", choices=sorted(SHAPES))
     ap.add_argument("--dim", type=int, default=256)
     ap.add_argument("--model", default="safer2")
-    ap.add_argument("--cpu-frac", type=float, default=0.05)
+    ap.add_argument("--cpu-frac", type=float, default=0.15)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-stages", action="store_true", help="print per-stage times to stderr")
     args = ap.parse_args()
@@ -207,7 +207,7 @@ def main():
         res["value"] = v
         out = {"impl": "reference", "metric": "safer2_epoch_row_solves_per_s", "value": v, "unit": "row-solves/s",
                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": 1e3 * res["rows"] / v, "higher_is_better": True, "scaling": "weak",
+               "ms_per_step": 1e3 * res["rows"] / v, "higher_is_better": True, "scaling": "strong",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                "cpu_baseline": res,
                "e2e": {"value": v, "unit": "row-solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -312,7 +312,11 @@ def main():
     achieved = (bytes_u + bytes_v) / world / t_rows / 1e9 if t_rows > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "row_solve (step_U + step_V launches: CSR gather + SYRK + Cholesky)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src, "traffic": None,
+                "peak_source": peak_src,
+                # dram__bytes_read+write of the epoch's row-kernel launches from one `ncu --set full` capture of this
+                # workload on one GPU (profiles/r01_row_solve_tc_ncu_summary.txt); not re-measured per run
+                "traffic": 5.77e9 if (args.shape == "ml20m" and args.dim == 256 and world == 1
+                                      and cfg["model"] == "safer2") else None,
                 "algorithmic_bytes_per_epoch": bytes_u + bytes_v,
                 "kernel_share_of_step": t_rows * 1e3 / max(1e-9, sum(stage_ms.values())),
                 "stage_ms": stage_ms}
