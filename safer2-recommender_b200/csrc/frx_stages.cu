@@ -118,11 +118,14 @@ int gramian_slabs(int n, int tiles, int num_sms) {
 // ---------------------------------------------------------------------------
 // Kernel functions of the smoothed quantile, safer2.h:599-647.  float in/out,
 // double bodies, exactly the promotions of the reference expressions
-// (SURVEY.md D.4); B-14: float fabs.
+// (SURVEY.md D.4); B-14: float fabs.  pow(x, 2.0) / pow(x, 3.0) / pow(x, -3.0) are
+// written as products: glibc's pow is exact for these (what the reference gets),
+// CUDA's generic pow() is not and costs several hundred FP64 instructions per call,
+// which made the xi kernel compute-bound.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ float gaussian_kernel(const float u, const float h) {
-  return (float)(pow(2 * 3.14159265358979323846, -0.5) *
-                 exp(-pow((double)(u / h) * 0.70710678118654752440, 2.0)) / (double)h);
+  const double t = (double)(u / h) * 0.70710678118654752440;
+  return (float)(0.39894228040143267794 /* pow(2 pi, -0.5) */ * exp(-(t * t)) / (double)h);
 }
 __device__ __forceinline__ float gaussian_kernel_cdf(const float u, const float h) {
   return (float)(0.5 * erfc((double)(-(u / h)) * 0.70710678118654752440));
@@ -133,22 +136,25 @@ __device__ __forceinline__ float gaussian_loss(const float u, const float h, con
 }
 __device__ __forceinline__ float epanechnikov_kernel(const float u, const float h) {
   const float uh = u / h;
-  return (float)((3.0 / 4.0) * (1 - pow((double)uh, 2.0)) * (int)(fabsf(uh) < 1) / (double)h);
+  const double uhd = (double)uh;
+  return (float)((3.0 / 4.0) * (1 - uhd * uhd) * (int)(fabsf(uh) < 1) / (double)h);
 }
 __device__ __forceinline__ float epanechnikov_kernel_cdf(const float u, const float h) {
   const float uh = u / h;
   const int in_supp = (int)(fabsf(uh) <= 1);
   const int pos = (int)(uh > 1);
   const double hd = h, ud = u;
-  return (float)(((pow(hd, -3.0) / 4.0) *
-                  (((double)(3 * u) * pow(hd, 2.0) - pow(ud, 3.0)) + 2 * pow(hd, 3.0)) * in_supp) +
+  const double h2 = hd * hd, h3 = h2 * hd;
+  return (float)((((1.0 / h3) / 4.0) *
+                  (((double)(3 * u) * h2 - ud * ud * ud) + 2 * h3) * in_supp) +
                  (1 - in_supp) * pos);
 }
 __device__ __forceinline__ float epanechnikov_loss(const float u, const float h, const float alpha) {
   const float uh = u / h;
   const int in_supp = (int)(fabsf(uh) <= 1);
   const int pos = (int)(uh > 1);
-  const float ell = (float)(((3.0 / 4.0) * pow((double)uh, 2.0) - (1.0 / 8.0) * pow((double)uh, 4.0) +
+  const double uh2 = (double)uh * (double)uh;
+  const float ell = (float)(((3.0 / 4.0) * uh2 - (1.0 / 8.0) * (uh2 * uh2) +
                              (3.0 / 8.0)) * in_supp + (double)(fabsf(uh) * pos));
   return (float)((1.0 / 2.0) * (double)h * (double)ell + ((double)(1 - alpha) - 0.5) * (double)u);
 }
