@@ -324,6 +324,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
   uint64_t* upd_bar = bars + 5;    // [1] trailing update complete
   uint64_t* col_bar = bars + 6;    // [4] columns 8q..8q+7 of the current diagonal factor are published
   uint64_t* ld_bar = bars + 10;    // [1] the diagonal warp has read its panel rows from TMEM
+  uint64_t* upd1_bar = bars + 11;  // [1] first batch of a trailing update (the next panel's columns of its M block)
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -340,6 +341,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
     mbar_init(upd_bar, 1);
     for (int q = 0; q < 4; ++q) mbar_init(&col_bar[q], 1);
     mbar_init(ld_bar, 1);
+    mbar_init(upd1_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == TC_MMA_WARP) {
@@ -569,8 +571,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
 #pragma unroll 1
     for (int pn = 0; pn < P; ++pn) {
       const int c0 = 32 * pn, c1 = c0 + 32;
-      if (pn > 0) {  // trailing update of the previous panel has landed in TMEM
-        mbar_wait(upd_bar, (upd_count - 1) & 1);
+      if (pn > 0) {
+        // The previous trailing update is issued in two batches: the diagonal warp only needs the first one
+        // (this panel's 32 columns of its own M block) and starts factoring while the rest still runs.
+        mbar_wait(warp == pn ? upd1_bar : upd_bar, (upd_count - 1) & 1);
         tc_fence_after();
       }
       FRX_DBG_LAP(2);  // exposed wait for the trailing update
@@ -683,7 +687,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
       FRX_DBG_LAP(6);  // wait for the diagonal warp + triangular solve (this warp)
       if (c1 < D) {
         if (is_row_warp && warp >= pn) {
-          // -- L panel rows as K-major tf32 hi/lo operand tiles --
+          // -- L panel rows as K-major tf32 hi/lo operand tiles (the previous update must be done reading them) --
+          if (pn > 0 && warp == pn) mbar_wait(upd_bar, (upd_count - 1) & 1);
           const int i = 32 * warp + lane;
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
@@ -707,22 +712,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
         if (warp == TC_MMA_WARP) {
           tc_fence_after();
           if (lane == 0) {
-            // A22 -= L21 L21^T on columns [c1, limit) of every M block that still has rows >= c1
+            // A22 -= L21 L21^T on columns [c1, limit) of every M block that still has rows >= c1, in two
+            // batches: (1) the next panel's 32 columns of the M block that holds the next diagonal block,
+            // (2) everything else.  (An M=128 MMA costs the same 93 cycles for N = 32 and N = 64, so the split
+            // adds tensor time, but that is hidden under the next diagonal factor.)
             const uint32_t hi_addr = sm_addr, lo_addr = sm_addr + L::kTileBytes;
+            const bool blk1 = D == 256 && c1 >= 128;  // M block of rows c1 .. c1+31
+            const uint32_t a_off = blk1 ? 128u * 128u : 0u, d_off = blk1 ? 256u : 0u;
+            constexpr uint32_t idesc32 = make_idesc_tf32(32, 1);
 #pragma unroll
             for (int ks = 0; ks < KT / 8; ++ks) {
               const uint32_t ko = ks * 32;
               const uint64_t b_hi = make_kmajor_desc(hi_addr + (uint32_t)c1 * 128 + ko);
               const uint64_t b_lo = make_kmajor_desc(lo_addr + (uint32_t)c1 * 128 + ko);
-              if (c1 < 128) {
-                const uint32_t idesc = make_idesc_tf32(128 - c1, 1);
-                const uint64_t a_hi = make_kmajor_desc(hi_addr + ko), a_lo = make_kmajor_desc(lo_addr + ko);
-                umma_tf32(tmem_base + (uint32_t)c1, a_hi, b_hi, idesc, 1u);
-                umma_tf32(tmem_base + (uint32_t)c1, a_hi, b_lo, idesc, 1u);
-                umma_tf32(tmem_base + (uint32_t)c1, a_lo, b_hi, idesc, 1u);
+              const uint64_t a_hi = make_kmajor_desc(hi_addr + a_off + ko), a_lo = make_kmajor_desc(lo_addr + a_off + ko);
+              umma_tf32(tmem_base + d_off + (uint32_t)c1, a_hi, b_hi, idesc32, 1u);
+              umma_tf32(tmem_base + d_off + (uint32_t)c1, a_hi, b_lo, idesc32, 1u);
+              umma_tf32(tmem_base + d_off + (uint32_t)c1, a_lo, b_hi, idesc32, 1u);
+            }
+            umma_commit(upd1_bar);
+            const int c2 = c1 + 32;
+            const int lim = blk1 ? 256 : 128;  // column limit of that M block
+#pragma unroll
+            for (int ks = 0; ks < KT / 8; ++ks) {
+              const uint32_t ko = ks * 32;
+              if (c2 < lim) {  // the remaining columns of the same M block
+                const uint32_t idesc = make_idesc_tf32(lim - c2, 1);
+                const uint64_t b_hi = make_kmajor_desc(hi_addr + (uint32_t)c2 * 128 + ko);
+                const uint64_t b_lo = make_kmajor_desc(lo_addr + (uint32_t)c2 * 128 + ko);
+                const uint64_t a_hi = make_kmajor_desc(hi_addr + a_off + ko), a_lo = make_kmajor_desc(lo_addr + a_off + ko);
+                umma_tf32(tmem_base + d_off + (uint32_t)c2, a_hi, b_hi, idesc, 1u);
+                umma_tf32(tmem_base + d_off + (uint32_t)c2, a_hi, b_lo, idesc, 1u);
+                umma_tf32(tmem_base + d_off + (uint32_t)c2, a_lo, b_hi, idesc, 1u);
               }
-              if (D == 256) {
+              if (D == 256 && !blk1) {  // rows 128..255, all columns from c1
                 const uint32_t idesc = make_idesc_tf32(256 - c1, 1);
+                const uint64_t b_hi = make_kmajor_desc(hi_addr + (uint32_t)c1 * 128 + ko);
+                const uint64_t b_lo = make_kmajor_desc(lo_addr + (uint32_t)c1 * 128 + ko);
                 const uint64_t a_hi = make_kmajor_desc(hi_addr + 128 * 128 + ko);
                 const uint64_t a_lo = make_kmajor_desc(lo_addr + 128 * 128 + ko);
                 umma_tf32(tmem_base + 256 + (uint32_t)c1, a_hi, b_hi, idesc, 1u);
