@@ -315,7 +315,7 @@ def main():
                 "peak_source": peak_src,
                 # dram__bytes_read+write of the epoch's row-kernel launches from one `ncu --set full` capture of this
                 # workload on one GPU (profiles/r01_row_solve_tc_ncu_summary.txt); not re-measured per run
-                "traffic": 5.77e9 if (args.shape == "ml20m" and args.dim == 256 and world == 1
+                "traffic": 5.79e9 if (args.shape == "ml20m" and args.dim == 256 and world == 1
                                       and cfg["model"] == "safer2") else None,
                 "algorithmic_bytes_per_epoch": bytes_u + bytes_v,
                 "kernel_share_of_step": t_rows * 1e3 / max(1e-9, sum(stage_ms.values())),
