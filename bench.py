@@ -280,8 +280,7 @@ def main():
         # H2D of this epoch's inputs from pinned host memory and D2H of the updated factors; with several
         # ranks each one moves the rows it owns (the blocks are all-gathered over NVLink after the upload)
         m.upload_factors_sharded(ds, Uh, Vh)
-        m.train(ds)
-        m.factors_sharded(ds, Uh, Vh)  # synchronises
+        m.train_to_host(ds, Uh, Vh)    # synchronises; the D2H of U runs under the item half-step
         sc = m.scalars()              # D2H of xi / weighted loss / mean z
     f1.record(stream)
     barrier()

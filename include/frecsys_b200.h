@@ -115,6 +115,10 @@ int frx_model_upload_factors(frx_model* m, const float* U, const float* V);
  * this is the per-process view of that array. */
 int frx_model_upload_factors_sharded(frx_model* m, frx_dataset* train, const float* U, const float* V);
 int frx_model_get_factors_sharded(frx_model* m, frx_dataset* train, float* U, float* V);
+/* Train() (below) followed by frx_model_get_factors_sharded, for a caller that keeps its factors in host
+ * memory like the reference does (recommender.h): the device->host copy of U is started as soon as the last
+ * user half-step of the epoch is final and runs under the item half-step.  Synchronous. */
+int frx_model_train_to_host(frx_model* m, frx_dataset* train, float* U, float* V);
 /* Initialize(const Dataset&) — safer2.h:819-838, safer2pp.h, erm_mf.h:573-587,
  * cvar_mf.h:710-726; a no-op for iALS / iALS++ (run_model.cc:246-257). */
 int frx_model_initialize(frx_model* m, frx_dataset* train);

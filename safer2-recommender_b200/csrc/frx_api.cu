@@ -46,6 +46,8 @@ struct frx_context {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t copy_stream = nullptr;  // device->host copies that overlap the rest of an epoch (frx_model_train_to_host)
+  cudaEvent_t copy_ev = nullptr;
   int num_sms = 148;
   long long launches = 0;
   float* gram_ws = nullptr;
@@ -133,6 +135,8 @@ struct frx_dataset {
 
 struct frx_model {
   frx_context* ctx = nullptr;
+  float* early_U_host = nullptr;  // frx_model_train_to_host: where U goes as soon as the user half-step is final
+  bool early_U_done = false;
   frx_config cfg;
   int num_users = 0, num_items = 0;
   float *U = nullptr, *V = nullptr, *G = nullptr, *Gz = nullptr;
@@ -195,6 +199,8 @@ extern "C" void frx_context_destroy(frx_context* c) {
   cudaFree(c->row_scratch);
   cudaFree(c->dws);
   cudaFree(c->status_dev);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->copy_ev) cudaEventDestroy(c->copy_ev);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -987,6 +993,30 @@ extern "C" int frx_model_initialize(frx_model* m, frx_dataset* ds) {
   return FRX_OK;
 }
 
+// U is final for this epoch once the last user half-step (and its all-gather) is on the stream: its
+// device->host copy (this rank's rows) runs on the copy stream under the item half-step.
+static int maybe_download_U(frx_model* m, frx_dataset* ds) {
+  if (!m->early_U_host || m->early_U_done) return FRX_OK;
+  frx_context* c = m->ctx;
+  if (!c->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->copy_ev, cudaEventDisableTiming));
+  }
+  const size_t d = m->cfg.dim;
+  size_t b = 0, e = (size_t)m->num_users;
+  if (c->world > 1) {
+    b = ds->by_user.rank_begin[c->rank];
+    e = c->rank == c->world - 1 ? (size_t)m->num_users : (size_t)ds->by_user.rank_begin[c->rank + 1];
+  }
+  CK(cudaEventRecord(c->copy_ev, c->stream));
+  CK(cudaStreamWaitEvent(c->copy_stream, c->copy_ev, 0));
+  if (e > b)
+    CK(cudaMemcpyAsync(m->early_U_host + b * d, m->U + b * d, sizeof(float) * (e - b) * d, cudaMemcpyDeviceToHost,
+                       c->copy_stream));
+  m->early_U_done = true;
+  return FRX_OK;
+}
+
 extern "C" int frx_model_train(frx_model* m, frx_dataset* ds) {
   frx_context* c = m->ctx;
   CK(cudaSetDevice(c->device));
@@ -999,6 +1029,7 @@ extern "C" int frx_model_train(frx_model* m, frx_dataset* ds) {
   switch (m->cfg.model) {
     case FRX_IALS:  // ials.h:187-224
       RC(stage_ials_step(m, ds, true, m->U, nullptr, nullptr));
+      RC(maybe_download_U(m, ds));
       RC(stage_ials_step(m, ds, false, m->V, nullptr, nullptr));
       RC(stage_item_gramian(m));  // ComputeUserLoss recomputes the Gramian, ials.h:371
       RC(stage_user_loss(m, ds, m->G, nullptr));
@@ -1014,6 +1045,7 @@ extern "C" int frx_model_train(frx_model* m, frx_dataset* ds) {
       break;
     case FRX_ERM_MF:  // erm_mf.h:257-301
       RC(stage_step_u(m, ds));
+      RC(maybe_download_U(m, ds));
       RC(stage_step_v(m, ds, m->U));
       RC(stage_item_gramian(m));
       RC(stage_user_loss(m, ds, m->G, nullptr));
@@ -1034,6 +1066,7 @@ extern "C" int frx_model_train(frx_model* m, frx_dataset* ds) {
       for (int t = 0; t < m->cfg.pd_iterations; ++t) {
         RC(stage_weights(m));
         RC(stage_step_u(m, ds));
+        if (t == m->cfg.pd_iterations - 1) RC(maybe_download_U(m, ds));
         RC(stage_step_v(m, ds, m->U));
         RC(stage_item_gramian(m));
         RC(stage_user_loss(m, ds, m->G, nullptr));
@@ -1058,6 +1091,24 @@ extern "C" int frx_model_train(frx_model* m, frx_dataset* ds) {
       RC(stage_xi(m, false));
       break;
   }
+  return FRX_OK;
+}
+
+// One Train() epoch for a caller whose factors live in host memory: on return U and V (this rank's rows
+// when there are several ranks, as frx_model_get_factors_sharded) are in the host arrays.  The copy of U
+// overlaps the item half-step for the models whose user factors are final after the user half-step.
+extern "C" int frx_model_train_to_host(frx_model* m, frx_dataset* ds, float* U, float* V) {
+  frx_context* c = m->ctx;
+  m->early_U_host = U;
+  m->early_U_done = false;
+  int rc = frx_model_train(m, ds);
+  const bool u_done = m->early_U_done;
+  m->early_U_host = nullptr;
+  m->early_U_done = false;
+  if (rc) return rc;
+  rc = frx_model_get_factors_sharded(m, ds, u_done ? nullptr : U, V);  // synchronises the main stream
+  if (rc) return rc;
+  if (u_done) CK(cudaStreamSynchronize(c->copy_stream));
   return FRX_OK;
 }
 

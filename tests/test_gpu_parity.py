@@ -334,6 +334,37 @@ def test_tensor_core_long_rows_are_split(pkg, O, ctx, name, cfg, d, long_side):
     ds.close()
 
 
+@pytest.mark.parametrize("name,cfg", [
+    ("safer2", dict(uobs_weight=0.004, reg=0.004, bandwidth=0.15, pd_iterations=2)),
+    ("ials", dict(uobs_weight=0.1, reg=0.003)),
+    ("cvar_mf", dict(uobs_weight=0.008, reg=0.002, stepsize=0.4)),
+])
+def test_train_to_host_equals_train_then_download(pkg, O, ctx, name, cfg):
+    """frx_model_train_to_host starts the device->host copy of U right after the last user half-step (on a
+    second stream, under the item half-step) for the models where U is final by then; the host arrays must
+    be bit-identical to Train() + GetFactors, also for a model that takes the plain path (CVaR-MF)."""
+    users, items = small_data(empty=False)
+    nu, ni = 400, 300
+    res = []
+    for mode in (0, 1):
+        ds = pkg.Dataset(ctx, users, items)
+        m = pkg.Model(ctx, nu, ni, model=name, dim=32, **cfg)
+        m.init_factors(3)
+        m.initialize(ds)
+        U = np.full((nu, 32), np.nan, np.float32)
+        V = np.full((ni, 32), np.nan, np.float32)
+        for _ in range(2):
+            if mode == 0:
+                m.train(ds)
+                m.factors(U, V)
+            else:
+                m.train_to_host(ds, U, V)
+        res.append((U.copy(), V.copy()))
+        m.close()
+        ds.close()
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+
+
 def test_multi_gpu_row_sharded_epoch():
     """2-rank NCCL run of tests/dist_parity.py (skipped on a 1-GPU box)."""
     import subprocess
