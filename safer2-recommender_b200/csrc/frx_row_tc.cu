@@ -1,27 +1,36 @@
 // Fused row kernel on 5th-generation tensor cores (tcgen05 + TMEM), D = 128 / 256.
 //
-// One CTA per row r of the side being solved; the d x d system never leaves the SM:
-//   phase A  A_r = sum_c s_c e_c e_c^T  (+ rhs = sum_c q_c e_c)
-//            16 loader warps gather the history rows (lane = history entry, 128 B per lane
-//            per load), split each fp32 into tf32 hi + lo and store them TRANSPOSED into
-//            K-major, 128B-swizzled operand tiles [feature][32 entries]; one thread issues
-//            tcgen05.mma kind::tf32 for hi*hi + hi*lo + lo*hi (error-compensated 3xTF32:
-//            fp32-level accuracy) into TMEM accumulators; lower-triangle tiles only.
-//            Two operand stages, mbarrier full/empty pipeline, tcgen05.commit frees a stage.
-//   phase B  in TMEM: M = a*A + b*G + reg*I, then a right-looking blocked Cholesky with
-//            32-wide panels.  Thread i owns matrix row i (tcgen05.ld gives it its 32 panel
-//            entries): the diagonal 32x32 block is factored by one warp with shuffles and
-//            inverted; the rows below do the triangular solve in registers; the L panel is
-//            written (tf32 hi/lo) as K-major operand tiles and the trailing update
-//            A22 -= L21 L21^T runs on the tensor cores with the a_negate bit.  The forward
-//            substitution is fused into the sweep; the back substitution uses the L panels
-//            kept in shared memory.
+// One persistent CTA per SM (16 warps, 128 registers per thread), one row r of the side being solved at
+// a time; the d x d system never leaves the SM (DESIGN.md 4.1 has the full description and the measured
+// cycle budget):
+//   set-up   alpha*G + beta*I of the row is written into the TMEM accumulators BEFORE the SYRK, by the
+//            warps that are idle during the back substitution of the previous row (row_scalars,
+//            tmem_init_system).
+//   phase A  S_r = sum_c s_c e_c e_c^T  (+ rhs = sum_c q_c e_c)
+//            15 loader warps take (32-entry tile, 32-feature slab) units round-robin: lane = history
+//            entry (128 B per lane per unit), split each fp32 into tf32 hi + lo and store them
+//            TRANSPOSED into K-major, 128B-swizzled operand tiles [feature][32 entries]; warp 15 issues
+//            tcgen05.mma kind::tf32 for hi*hi + hi*lo + lo*hi (error-compensated 3xTF32: fp32-level
+//            accuracy) onto the TMEM accumulators; lower-triangle M blocks only.  Two operand stages,
+//            mbarrier full/empty pipeline, tcgen05.commit frees a stage.
+//   phase B  right-looking blocked Cholesky in TMEM with 32-wide panels.  Thread i owns matrix row i
+//            (tcgen05.ld gives it its 32 panel entries): the diagonal 32x32 block is factored by one
+//            warp (columns published through shared memory, shuffle shortcut for the next pivot); the
+//            rows below run their triangular solve behind that sweep (mbarrier per 8 columns); the L
+//            panel is written (tf32 hi/lo) as K-major operand tiles and the trailing update
+//            A22 -= L21 L21^T runs on the tensor cores with the a_negate bit, in two committed batches
+//            (the next diagonal block's columns first).  The forward substitution is fused into the
+//            sweep; the back substitution is column-oriented over the L panels kept in shared memory.
+//   long rows (> FRX_SPLIT_MIN entries) are cut into pieces: MODE 1 dumps per-piece partial sums, MODE 2
+//            solves such a row from the sum of its pieces, MODE 0 is the ordinary row.
 //
-// Hardware conventions were established with tools/tc_probe.cu on a B200:
+// Hardware conventions were established with tools/tc_probe.cu / tc_rate.cu / lat_probe.cu on a B200:
 //  * kind::tf32 works with K-major operands (SWIZZLE_128B, SBO = 1024 B, K step = +32 B on
 //    the descriptor start address); MN-major tf32 operands produce zeros, hence the transpose.
 //  * the MMA ignores the low 13 mantissa bits of fp32 inputs (truncation).
 //  * tcgen05.ld/st 32x32b: warp w touches TMEM lanes 32*(w%4)..+31, thread = accumulator row.
+//  * an M=128 MMA takes 93 / 106 / 170 cycles for N <= 64 / 128 / 256; the issuing thread blocks while
+//    the (shallow) tensor queue is full.
 // Restates ials.h:88-144, safer2.h:104-163 and safer2.h:166-221 (incl. the stale-tail quirk).
 #include "frx_kernels.cuh"
 #include <cstdint>
@@ -312,7 +321,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
   uint8_t* opnd_hi = sm;                      // phase B operand tiles (alias stage 0)
   uint8_t* opnd_lo = sm + L::kTileBytes;
   float* Lst = reinterpret_cast<float*>(sm + L::kLstOff);
-  float* rhs_part = reinterpret_cast<float*>(sm + L::kRhsOff);
   float* Ld = reinterpret_cast<float*>(sm + L::kLdOff);
   float* wsum = reinterpret_cast<float*>(sm + L::kWsumOff);
   float* yS = reinterpret_cast<float*>(sm + L::kYOff);
@@ -592,16 +600,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
       float* LdT = Ld + (pn & 1) * 1024;  // L11 transposed: LdT[k * 32 + m] = L11[m][k] (double-buffered by panel parity)
       float* rd = rdiag + (pn & 1) * 32;  // 1 / L11[k][k]
       if (warp == pn) {
-        // -- diagonal block: right-looking Cholesky by shuffles (lane = row).  The block is symmetric, so the
-        //    pivot row is read from lane k (S[k][j]) and its shuffles do not wait for the rsqrt; the rhs is
-        //    carried along as an extra column so that y = inv(L11) b comes out of the same sweep. --
+        // -- diagonal block: right-looking Cholesky, lane = row.  Column k is scaled, published to shared
+        //    memory with one store and read back as broadcast float4s for the rank-1 update; the next pivot
+        //    (lane k+1 computes it from its own column-k entry) and the next column take shuffles so that
+        //    the shared-memory round trip is off the dependency chain; the rhs is carried along as an
+        //    extra column so that y = inv(L11) b comes out of the same sweep.  (Measured: the pivot chain
+        //    FMUL -> FFMA -> SHFL -> MUFU.RSQ -> FMUL is ~52 cycles, one step ~96 with the in-order issue
+        //    of the update; publishing the pivot ROW instead of the column is slower.) --
         long long dgt0 = 0;
         if (p.dbg && lane == 0) dgt0 = clock64();
-        // Right-looking Cholesky by shuffles, lane = row.  The block is symmetric, so the pivot row is read
-        // from lane k (S[k][j]) and the next pivot comes from the lane's OWN column-k entry
-        // (S[k+1][k] = S[k][k+1]): its shuffle + rsqrt are issued before the bulk rank-1 update of step k.
-        // (Measured alternatives: publishing the pivot row through shared memory is slower; a single warp
-        // sustains ~4 cycles per instruction here, the 256 sequential pivots of a row are the latency floor.)
         float rs;
         bool bad_pivot;  // warp-uniform; reported once after the sweep so that the loop stays branch-free
         {
