@@ -4,10 +4,20 @@
 // library can build its device-resident CSR/CSC from it (frx_dataset_create).
 #pragma once
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
+#include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "frecsys/logging.h"
@@ -15,13 +25,21 @@
 
 namespace frecsys {
 
+// Ingest.  The reference parses with getline + substr + atoi and inserts every tuple into
+// two hash maps of vectors (dataset.h:71-99): minutes at the ML-20M / MSD shapes, far longer than a GPU
+// epoch.  Here the file is mmap'ed and parsed by all host threads into the flat tuple list in FILE order
+// (what frx_dataset_create turns into the bit-exact device CSR/CSC); the by_user()/by_item() hash maps of
+// the reference interface are built lazily, only for a caller that asks for them (EvaluateDataset's
+// `eval_by_user` argument).  Line semantics are the reference's: the header line is dropped, every
+// following line (also an empty one) yields one tuple, user = atoi(text before the first ','),
+// item = atoi(text after it); a line without ',' gives atoi(line) for both (substr(npos + 1)).
 class Dataset {
 public:
   explicit Dataset(const std::string& filename);
   // Builds a Dataset from tuple arrays (synthetic data, tests).
   Dataset(const int* users, const int* items, int n);
-  const SpMatrix& by_user() const { return by_user_; }
-  const SpMatrix& by_item() const { return by_item_; }
+  const SpMatrix& by_user() const { build_maps(); return maps_->by_user; }
+  const SpMatrix& by_item() const { build_maps(); return maps_->by_item; }
   const int max_user() const { return max_user_; }
   const int max_item() const { return max_item_; }
   const int num_tuples() const { return num_tuples_; }
@@ -30,44 +48,125 @@ public:
   const std::vector<int>& items() const { return items_; }
 
 private:
-  void add(int user, int item) {  // dataset.h:86-91
-    by_user_[user].push_back({item, num_tuples_});
-    by_item_[item].push_back({user, num_tuples_});
-    users_.push_back(user);
-    items_.push_back(item);
-    max_user_ = std::max(max_user_, user);
-    max_item_ = std::max(max_item_, item);
-    ++num_tuples_;
+  struct Maps {
+    std::once_flag once;
+    SpMatrix by_user, by_item;
+  };
+  // atoi on [b, e): leading white space, optional sign, digits (no locale, no overflow handling: like atoi).
+  static int parse_int(const char* b, const char* e) {
+    while (b < e && (*b == ' ' || (*b >= '\t' && *b <= '\r'))) ++b;
+    bool neg = false;
+    if (b < e && (*b == '-' || *b == '+')) { neg = *b == '-'; ++b; }
+    long v = 0;
+    while (b < e && *b >= '0' && *b <= '9') { v = v * 10 + (*b - '0'); ++b; }
+    return (int)(neg ? -v : v);
+  }
+  static void parse_range(const char* b, const char* e, std::vector<int>* us, std::vector<int>* is) {
+    while (b < e) {
+      const char* nl = static_cast<const char*>(memchr(b, '\n', (size_t)(e - b)));
+      const char* le = nl ? nl : e;
+      const char* comma = static_cast<const char*>(memchr(b, ',', (size_t)(le - b)));
+      us->push_back(parse_int(b, comma ? comma : le));
+      is->push_back(comma ? parse_int(comma + 1, le) : parse_int(b, le));
+      b = nl ? nl + 1 : e;
+    }
+  }
+  void parse(const char* data, size_t size);
+  void finish() {
+    num_tuples_ = (int)users_.size();
+    for (int t = 0; t < num_tuples_; ++t) {
+      max_user_ = std::max(max_user_, users_[t]);
+      max_item_ = std::max(max_item_, items_[t]);
+    }
+    log_summary();
+  }
+  void build_maps() const {  // dataset.h:86-91
+    std::call_once(maps_->once, [this] {
+      for (int t = 0; t < num_tuples_; ++t) {
+        maps_->by_user[users_[t]].push_back({items_[t], t});
+        maps_->by_item[items_[t]].push_back({users_[t], t});
+      }
+    });
+  }
+  static size_t distinct(const std::vector<int>& ids, int max_id) {
+    if (max_id < 0) return 0;
+    std::vector<char> seen((size_t)max_id + 1, 0);
+    size_t n = 0;
+    for (int v : ids)
+      if (v >= 0 && !seen[v]) { seen[v] = 1; ++n; }
+    return n;
   }
   void log_summary() const {  // dataset.h:94-98
-    LOG(INFO) << "max_user=" << max_user() << "\tmax_item=" << max_item() << "\tdistinct user=" << by_user_.size()
-              << "\tdistinct item=" << by_item_.size() << "\tnum_tuples=" << num_tuples();
+    LOG(INFO) << "max_user=" << max_user() << "\tmax_item=" << max_item() << "\tdistinct user=" << distinct(users_, max_user_)
+              << "\tdistinct item=" << distinct(items_, max_item_) << "\tnum_tuples=" << num_tuples();
   }
-  SpMatrix by_user_;
-  SpMatrix by_item_;
+  std::shared_ptr<Maps> maps_ = std::make_shared<Maps>();
   std::vector<int> users_, items_;
   int max_user_ = -1;
   int max_item_ = -1;
   int num_tuples_ = 0;
 };
 
-inline Dataset::Dataset(const std::string& filename) {
-  std::ifstream infile(filename);
-  std::string line;
-  // Discard header (the reference asserts on it, dataset.h:80).
-  if (!std::getline(infile, line)) throw std::runtime_error("frecsys::Dataset: cannot read " + filename);
-  while (std::getline(infile, line)) {
-    int pos = line.find(',');
-    int user = std::atoi(line.substr(0, pos).c_str());
-    int item = std::atoi(line.substr(pos + 1).c_str());
-    add(user, item);
+inline void Dataset::parse(const char* data, size_t size) {
+  // Discard the header line (the reference asserts on it, dataset.h:80).
+  const char* end = data + size;
+  const char* body = static_cast<const char*>(memchr(data, '\n', size));
+  body = body ? body + 1 : end;
+  const size_t n = (size_t)(end - body);
+  unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+  if (n < (1u << 20)) nt = 1;
+  std::vector<const char*> cut(nt + 1, end);
+  cut[0] = body;
+  for (unsigned k = 1; k < nt; ++k) {  // chunk boundaries moved forward to the next line start
+    const char* p = body + n * k / nt;
+    if (p < cut[k - 1]) p = cut[k - 1];
+    const char* nl = static_cast<const char*>(memchr(p, '\n', (size_t)(end - p)));
+    cut[k] = nl ? nl + 1 : end;
   }
-  log_summary();
+  std::vector<std::vector<int>> us(nt), is(nt);
+  std::vector<std::thread> th;
+  for (unsigned k = 0; k < nt; ++k)
+    th.emplace_back([&, k] {
+      us[k].reserve((size_t)(cut[k + 1] - cut[k]) / 8 + 16);
+      is[k].reserve((size_t)(cut[k + 1] - cut[k]) / 8 + 16);
+      parse_range(cut[k], cut[k + 1], &us[k], &is[k]);
+    });
+  for (auto& t : th) t.join();
+  size_t total = 0;
+  for (unsigned k = 0; k < nt; ++k) total += us[k].size();
+  users_.reserve(total);
+  items_.reserve(total);
+  for (unsigned k = 0; k < nt; ++k) {
+    users_.insert(users_.end(), us[k].begin(), us[k].end());
+    items_.insert(items_.end(), is[k].begin(), is[k].end());
+  }
+}
+
+inline Dataset::Dataset(const std::string& filename) {
+  const int fd = ::open(filename.c_str(), O_RDONLY);
+  if (fd < 0) throw std::runtime_error("frecsys::Dataset: cannot read " + filename);
+  struct stat st;
+  if (fstat(fd, &st) != 0) { ::close(fd); throw std::runtime_error("frecsys::Dataset: cannot stat " + filename); }
+  const size_t size = (size_t)st.st_size;
+  if (size == 0) { ::close(fd); throw std::runtime_error("frecsys::Dataset: cannot read " + filename); }
+  void* map = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+  if (map != MAP_FAILED) {
+    parse(static_cast<const char*>(map), size);
+    munmap(map, size);
+    ::close(fd);
+  } else {  // not mappable (pipe, odd file system): read it
+    ::close(fd);
+    std::ifstream infile(filename, std::ios::binary);
+    std::string all((std::istreambuf_iterator<char>(infile)), std::istreambuf_iterator<char>());
+    parse(all.data(), all.size());
+  }
+  finish();
 }
 
 inline Dataset::Dataset(const int* users, const int* items, int n) {
-  for (int t = 0; t < n; ++t) add(users[t], items[t]);
-  log_summary();
+  users_.assign(users, users + n);
+  items_.assign(items, items + n);
+  finish();
 }
 
 }  // namespace frecsys
