@@ -8,6 +8,7 @@
 // call and keeps no reference, recommender.h:55 — we key the cache on the object's address and
 // tuple count).  There is no CPU fallback: if the library or a GPU is missing, construction throws.
 #pragma once
+#include <algorithm>
 
 #include <chrono>
 #include <cstdio>
@@ -139,6 +140,30 @@ protected:
     return {sc[0], sc[1], sc[2]};
   }
   void initialize_on_device(const Dataset& data) { check(frx_model_initialize(model_, device_dataset(data)), "frx_model_initialize"); }
+  // "VaR: .. CVaR: .." and "Min: .. Mean: .. Max: .." of --print_var_stats (safer2.h:303-319, safer2pp.h),
+  // restated on the host from the per-user loss and dual weights of the finished epoch, with the reference's
+  // types: Q = size * alpha as a float, nth_element of -loss at (ptrdiff_t)Q, float running sum over i <= Q,
+  // divided by Q.  (With pd_iterations > 1 the reference prints inside every primal-dual iteration; here the
+  // epoch is one call, so the line is printed once, for the last iteration.)
+  void PrintVarStats(float alpha) const {
+    std::vector<float> z(num_users_), loss(num_users_);
+    check(frx_model_get_state(model_, z.data(), loss.data(), nullptr, nullptr, nullptr, nullptr), "frx_model_get_state");
+    std::vector<float> vals;
+    vals.reserve(loss.size());
+    for (size_t i = 0; i < loss.size(); i++) vals.push_back(-loss[i]);
+    if (vals.empty()) return;
+    auto const Q = vals.size() * alpha;
+    std::nth_element(vals.begin(), vals.begin() + (std::ptrdiff_t)Q, vals.end());
+    float acc = 0;
+    for (int i = 0; i <= Q && i < (int)vals.size(); i++) acc += -vals[i];
+    LOG(INFO) << "VaR: " << -vals[(int)Q] << " CVaR: " << acc / Q;
+    float mn = z[0], mx = z[0];
+    float sum = 0;  // Eigen's mean() of a VectorXf: float accumulation
+    for (float v : z) { mn = std::min(mn, v); mx = std::max(mx, v); sum += v; }
+    char buf[128];
+    std::snprintf(buf, sizeof buf, "Min: %.3f, Mean: %.3f, Max: %.3f", mn, sum / (float)z.size(), mx);
+    LOG(INFO) << buf;
+  }
   virtual bool stats_after_train() const { return false; }
   virtual void after_train() {}
 

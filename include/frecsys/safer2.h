@@ -37,6 +37,7 @@ protected:
   void after_train() override {
     const Scalars s = scalars();
     LOG(INFO) << "Weighted Loss: " << s.weighted_loss;  // safer2.h:300-301 (last primal-dual iteration)
+    if (print_varstats_) PrintVarStats(cfg_.alpha);  // safer2.h:303-319
     LOG(INFO) << "Xi:" << s.xi;                         // safer2.h:332
   }
 };

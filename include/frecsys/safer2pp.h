@@ -25,6 +25,7 @@ protected:
   void after_train() override {
     const Scalars s = scalars();
     LOG(INFO) << "Weighted Loss: " << s.weighted_loss;
+    if (print_varstats_) PrintVarStats(cfg_.alpha);  // safer2pp.h
     LOG(INFO) << "Xi:" << s.xi;
   }
 };

@@ -399,6 +399,8 @@ def test_run_model_cli_reference_thresholds(name, flags, epochs):
     cmd = [exe, "--model_name", name, "--dim", "8", "--stdev", "0.1", "--print_train_stats", "1", "--epoch", str(epochs),
            "--train_data", helpers.fixture_csv("train"), "--test_train_data", helpers.fixture_csv("validation_tr"),
            "--test_test_data", helpers.fixture_csv("validation_te"), "--init_seed", "1"] + flags.split()
+    if name in ("safer2", "safer2pp"):
+        cmd += ["--print_var_stats", "1"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     log = out.stderr
@@ -408,6 +410,16 @@ def test_run_model_cli_reference_thresholds(name, flags, epochs):
     assert ndcg20 >= 0.2, ndcg20
     if name in ("safer2", "safer2pp"):
         assert "Initial Xi:" in log and "Weighted Loss:" in log and "Xi:" in log
+        # --print_var_stats (safer2.h:303-319): one "VaR/CVaR" and one "Min/Mean/Max" line per epoch; CVaR is the
+        # mean of the worst alpha-tail of the user losses, so it is at least the VaR; the dual weights average
+        # to alpha within the reference's own test bound (safer2_test.cc:135)
+        var = re.findall(r"VaR: ([-\d.e+]+) CVaR: ([-\d.e+]+)", log)
+        mmm = re.findall(r"Min: ([\d.]+), Mean: ([\d.]+), Max: ([\d.]+)", log)
+        assert len(var) == epochs and len(mmm) == epochs
+        v, c = float(var[-1][0]), float(var[-1][1])
+        assert np.isfinite(v) and np.isfinite(c) and c >= v > 0
+        mn, mean, mx = (float(x) for x in mmm[-1])
+        assert 0.0 <= mn <= mean <= mx <= 1.0 and abs(mean - 0.3) <= 0.02
 
 
 @pytest.mark.parametrize("d", [64, 512])
