@@ -130,6 +130,9 @@ public:
   void GetFactors(MatrixXf* U, MatrixXf* V) const {
     check(frx_model_get_factors(model_, U ? U->data() : nullptr, V ? V->data() : nullptr), "get_factors");
   }
+  // Checkpoint / resume (the reference has none): see frx_model_save / frx_model_load.
+  void SaveCheckpoint(const std::string& path) const { check(frx_model_save(model_, path.c_str()), "frx_model_save"); }
+  void LoadCheckpoint(const std::string& path) { check(frx_model_load(model_, path.c_str()), "frx_model_load"); }
   frx_model* handle() const { return model_; }
 
 protected:

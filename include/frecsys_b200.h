@@ -119,6 +119,12 @@ int frx_model_get_factors_sharded(frx_model* m, frx_dataset* train, float* U, fl
  * memory like the reference does (recommender.h): the device->host copy of U is started as soon as the last
  * user half-step of the epoch is final and runs under the item half-step.  Synchronous. */
 int frx_model_train_to_host(frx_model* m, frx_dataset* train, float* U, float* V);
+/* Checkpoint / resume (the reference has none): factors, dual weights, per-user loss, history
+ * sizes, item regularisation sums, xi, running means and the ComputeXi call counter (SNR seeds).  A model
+ * created with the same kind, dim and sizes and loaded from the file continues bit-identically; no
+ * Initialize() call is needed (or wanted: it would recompute xi from the mean loss, safer2.h:822). */
+int frx_model_save(frx_model* m, const char* path);
+int frx_model_load(frx_model* m, const char* path);
 /* Initialize(const Dataset&) — safer2.h:819-838, safer2pp.h, erm_mf.h:573-587,
  * cvar_mf.h:710-726; a no-op for iALS / iALS++ (run_model.cc:246-257). */
 int frx_model_initialize(frx_model* m, frx_dataset* train);

@@ -19,7 +19,7 @@ MODEL_IDS = {"ials": 0, "ialspp": 1, "erm_mf": 2, "cvar_mf": 3, "safer2": 4, "sa
 
 EXPORTS = [
     "frx_last_error", "frx_context_create", "frx_context_destroy", "frx_context_sync",
-    "frx_context_stream", "frx_comm_unique_id", "frx_context_init_comm", "frx_partition_rows", "frx_dataset_create", "frx_model_upload_factors_sharded", "frx_model_get_factors_sharded", "frx_model_train_to_host",
+    "frx_context_stream", "frx_comm_unique_id", "frx_context_init_comm", "frx_partition_rows", "frx_dataset_create", "frx_model_upload_factors_sharded", "frx_model_get_factors_sharded", "frx_model_train_to_host", "frx_model_save", "frx_model_load",
     "frx_dataset_destroy", "frx_dataset_info", "frx_dataset_get_csr", "frx_model_create",
     "frx_model_destroy", "frx_model_init_factors", "frx_model_set_factors", "frx_model_get_factors", "frx_model_upload_factors",
     "frx_model_initialize", "frx_model_train", "frx_model_stage", "frx_model_get_state",
@@ -107,6 +107,8 @@ def lib():
     L.frx_model_upload_factors_sharded.argtypes = [vp, vp, fp, fp]
     L.frx_model_get_factors_sharded.argtypes = [vp, vp, fp, fp]
     L.frx_model_train_to_host.argtypes = [vp, vp, fp, fp]
+    L.frx_model_save.argtypes = [vp, C.c_char_p]
+    L.frx_model_load.argtypes = [vp, C.c_char_p]
     L.frx_model_initialize.argtypes = [vp, vp]
     L.frx_model_train.argtypes = [vp, vp]
     L.frx_model_stage.argtypes = [vp, vp, C.c_int]
@@ -272,6 +274,12 @@ class Model:
 
     def initialize(self, ds):
         _check(lib().frx_model_initialize(self.h, ds.h))
+
+    def save(self, path):
+        _check(lib().frx_model_save(self.h, os.fsencode(path)))
+
+    def load(self, path):
+        _check(lib().frx_model_load(self.h, os.fsencode(path)))
 
     def train_to_host(self, ds, U, V):
         """One epoch, then U and V (this rank's rows) in the host arrays; the copy of U overlaps the item half-step."""

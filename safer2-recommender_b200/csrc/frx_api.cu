@@ -1165,6 +1165,70 @@ extern "C" int frx_model_set_state(frx_model* m, const float* z, const float* lo
   return FRX_OK;
 }
 
+// Checkpoint (the reference has none).  Everything an epoch reads that is not recomputed
+// from the data set each time: factors, dual weights, per-user loss, history sizes, item regularisation
+// sums, xi and the running means, and the ComputeXi call counter (it seeds the SNR subsamples).  The item
+// Gramian is recomputed from V on load (same kernel, same bits).  Replicated state: with several ranks
+// every rank writes / reads the same content.
+static const char kCkptMagic[8] = {'F', 'R', 'X', 'C', 'K', 'P', 'T', '1'};
+
+extern "C" int frx_model_save(frx_model* m, const char* path) {
+  frx_context* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  const size_t d = m->cfg.dim, nu = m->num_users, ni = m->num_items;
+  std::vector<float> buf(nu * d + ni * d + 3 * nu + ni + 4);
+  float* p = buf.data();
+  const struct { const float* dev; size_t n; } parts[] = {{m->U, nu * d}, {m->V, ni * d}, {m->z, nu}, {m->loss, nu},
+                                                          {m->hist_size, nu}, {m->item_reg, ni}, {m->scal, 4}};
+  for (auto& q : parts) {
+    CK(cudaMemcpyAsync(p, q.dev, sizeof(float) * q.n, cudaMemcpyDeviceToHost, c->stream));
+    p += q.n;
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(FRX_ERR_ARG, "cannot open %s for writing", path);
+  const int hdr[5] = {m->cfg.model, m->cfg.dim, m->num_users, m->num_items, m->xi_calls};
+  bool ok = fwrite(kCkptMagic, 1, 8, f) == 8 && fwrite(hdr, sizeof(int), 5, f) == 5 &&
+            fwrite(buf.data(), sizeof(float), buf.size(), f) == buf.size();
+  ok = (fclose(f) == 0) && ok;
+  return ok ? FRX_OK : fail(FRX_ERR_ARG, "short write to %s", path);
+}
+
+extern "C" int frx_model_load(frx_model* m, const char* path) {
+  frx_context* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(FRX_ERR_ARG, "cannot open %s", path);
+  char magic[8];
+  int hdr[5];
+  if (fread(magic, 1, 8, f) != 8 || memcmp(magic, kCkptMagic, 8) != 0 || fread(hdr, sizeof(int), 5, f) != 5) {
+    fclose(f);
+    return fail(FRX_ERR_ARG, "%s is not a frecsys_b200 checkpoint", path);
+  }
+  if (hdr[0] != m->cfg.model || hdr[1] != m->cfg.dim || hdr[2] != m->num_users || hdr[3] != m->num_items) {
+    fclose(f);
+    return fail(FRX_ERR_ARG, "checkpoint %s is for model %d dim %d %d x %d, this model is %d dim %d %d x %d", path, hdr[0],
+                hdr[1], hdr[2], hdr[3], m->cfg.model, m->cfg.dim, m->num_users, m->num_items);
+  }
+  const size_t d = m->cfg.dim, nu = m->num_users, ni = m->num_items;
+  std::vector<float> buf(nu * d + ni * d + 3 * nu + ni + 4);
+  const bool ok = fread(buf.data(), sizeof(float), buf.size(), f) == buf.size();
+  fclose(f);
+  if (!ok) return fail(FRX_ERR_ARG, "checkpoint %s is truncated", path);
+  const float* p = buf.data();
+  const struct { float* dev; size_t n; } parts[] = {{m->U, nu * d}, {m->V, ni * d}, {m->z, nu}, {m->loss, nu},
+                                                    {m->hist_size, nu}, {m->item_reg, ni}, {m->scal, 4}};
+  for (auto& q : parts) {
+    CK(cudaMemcpyAsync(q.dev, p, sizeof(float) * q.n, cudaMemcpyHostToDevice, c->stream));
+    p += q.n;
+  }
+  int rc = gramian_into(m, m->V, m->num_items, 0, m->cfg.dim, 0, m->cfg.dim, nullptr, m->G);
+  if (rc) return rc;
+  m->xi_calls = hdr[4];
+  CK(cudaStreamSynchronize(c->stream));  // buf goes out of scope
+  return FRX_OK;
+}
+
 extern "C" int frx_model_last_snr(frx_model* m, int* n_iters, int* n_samples, int* out) {
   *n_iters = (int)m->last_snr.size();
   *n_samples = m->last_snr.empty() ? 0 : (int)m->last_snr[0].size();

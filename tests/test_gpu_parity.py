@@ -365,6 +365,42 @@ def test_train_to_host_equals_train_then_download(pkg, O, ctx, name, cfg):
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
 
 
+@pytest.mark.parametrize("name,cfg", [
+    ("safer2", dict(uobs_weight=0.004, reg=0.004, bandwidth=0.15, use_snr=1, sampling_ratio=0.5, snr_seed=9)),
+    ("safer2pp", dict(uobs_weight=0.004, reg=0.004, bandwidth=0.15, block_size=8)),
+    ("cvar_mf", dict(uobs_weight=0.008, reg=0.002, stepsize=0.4)),
+])
+def test_checkpoint_resume_is_bit_identical(pkg, O, ctx, tmp_path, name, cfg):
+    """Train 2 epochs, save, train 1 more; a fresh model loaded from the file (no Initialize) and trained 1
+    epoch must give the same factors, z, loss and xi bit for bit — including the SNR subsample sequence,
+    which is seeded by the ComputeXi call counter kept in the checkpoint."""
+    users, items = small_data(empty=False)
+    nu, ni = 400, 300
+    ds = pkg.Dataset(ctx, users, items)
+    a = pkg.Model(ctx, nu, ni, model=name, dim=16, **cfg)
+    a.init_factors(21)
+    a.initialize(ds)
+    a.train(ds)
+    a.train(ds)
+    path = os.path.join(str(tmp_path), "ckpt.bin")
+    a.save(path)
+    a.train(ds)
+    b = pkg.Model(ctx, nu, ni, model=name, dim=16, **cfg)
+    b.load(path)
+    b.train(ds)
+    Ua, Va = a.factors()
+    Ub, Vb = b.factors()
+    sa, sb = a.state(), b.state()
+    assert np.array_equal(Ua, Ub) and np.array_equal(Va, Vb)
+    assert np.array_equal(sa["z"], sb["z"]) and np.array_equal(sa["loss"], sb["loss"]) and sa["xi"] == sb["xi"]
+    c = pkg.Model(ctx, nu, ni, model=name, dim=32, **cfg)
+    with pytest.raises(Exception):
+        c.load(path)   # wrong dim
+    for m in (a, b, c):
+        m.close()
+    ds.close()
+
+
 def test_multi_gpu_row_sharded_epoch():
     """2-rank NCCL run of tests/dist_parity.py (skipped on a 1-GPU box)."""
     import subprocess
