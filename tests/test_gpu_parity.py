@@ -401,6 +401,31 @@ def test_checkpoint_resume_is_bit_identical(pkg, O, ctx, tmp_path, name, cfg):
     ds.close()
 
 
+@pytest.mark.parametrize("name,cfg", [
+    ("ials", dict(uobs_weight=0.1, reg=0.003)),
+    ("safer2", dict(uobs_weight=0.004, reg=0.004, bandwidth=0.15)),
+])
+def test_use_cg_flag_agrees_with_the_reference_cg_solve(pkg, O, ctx, name, cfg):
+    """--use_cg 1 (ials.h:134-138, safer2.h:152-157,211-215): the reference solves the same SPD system with
+    Jacobi-preconditioned CG to tolerance 1e-10; the CUDA path accepts the flag and solves by Cholesky.  Both
+    are the solution of the same system to fp32 accuracy, so the oracle's CG epoch and the CUDA epoch must
+    agree within the factor tolerance."""
+    users, items = small_data()
+    nu, ni = 400, 300
+    ods, om, ds, m = make_pair(pkg, O, ctx, users, items, nu, ni, model=name, dim=32, use_cg=1, cg_tol=1e-10,
+                               cg_max_it=100, **cfg)
+    om.initialize(ods)
+    m.initialize(ds)
+    om.train(ods)
+    m.train(ds)
+    U, V = m.factors()
+    Uo, Vo = om.factors()
+    assert rel_fro(U, Uo) < FACTOR_TOL, rel_fro(U, Uo)
+    assert rel_fro(V, Vo) < FACTOR_TOL, rel_fro(V, Vo)
+    m.close()
+    ds.close()
+
+
 def test_multi_gpu_row_sharded_epoch():
     """2-rank NCCL run of tests/dist_parity.py (skipped on a 1-GPU box)."""
     import subprocess
