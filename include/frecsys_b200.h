@@ -116,8 +116,8 @@ int frx_model_upload_factors(frx_model* m, const float* U, const float* V);
 int frx_model_upload_factors_sharded(frx_model* m, frx_dataset* train, const float* U, const float* V);
 int frx_model_get_factors_sharded(frx_model* m, frx_dataset* train, float* U, float* V);
 /* Train() (below) followed by frx_model_get_factors_sharded, for a caller that keeps its factors in host
- * memory like the reference does (recommender.h): the device->host copy of U is started as soon as the last
- * user half-step of the epoch is final and runs under the item half-step.  Synchronous. */
+ * memory like the reference does (recommender.h): the device->host copies of U and V are started as soon as
+ * their last half-step of the epoch is final and run under the rest of the epoch.  Synchronous. */
 int frx_model_train_to_host(frx_model* m, frx_dataset* train, float* U, float* V);
 /* Checkpoint / resume (the reference has none): factors, dual weights, per-user loss, history
  * sizes, item regularisation sums, xi, running means and the ComputeXi call counter (SNR seeds).  A model

@@ -135,8 +135,9 @@ struct frx_dataset {
 
 struct frx_model {
   frx_context* ctx = nullptr;
-  float* early_U_host = nullptr;  // frx_model_train_to_host: where U goes as soon as the user half-step is final
-  bool early_U_done = false;
+  float* early_U_host = nullptr;  // frx_model_train_to_host: where U / V go as soon as their half-step is final
+  float* early_V_host = nullptr;
+  bool early_U_done = false, early_V_done = false;
   frx_config cfg;
   int num_users = 0, num_items = 0;
   float *U = nullptr, *V = nullptr, *G = nullptr, *Gz = nullptr;
@@ -995,27 +996,33 @@ extern "C" int frx_model_initialize(frx_model* m, frx_dataset* ds) {
 
 // U is final for this epoch once the last user half-step (and its all-gather) is on the stream: its
 // device->host copy (this rank's rows) runs on the copy stream under the item half-step.
-static int maybe_download_U(frx_model* m, frx_dataset* ds) {
-  if (!m->early_U_host || m->early_U_done) return FRX_OK;
+static int maybe_download(frx_model* m, frx_dataset* ds, bool item_side) {
+  float* host = item_side ? m->early_V_host : m->early_U_host;
+  bool& done = item_side ? m->early_V_done : m->early_U_done;
+  if (!host || done) return FRX_OK;
   frx_context* c = m->ctx;
   if (!c->copy_stream) {
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->copy_ev, cudaEventDisableTiming));
   }
   const size_t d = m->cfg.dim;
-  size_t b = 0, e = (size_t)m->num_users;
+  const Csr& side = item_side ? ds->by_item : ds->by_user;
+  const size_t total = item_side ? (size_t)m->num_items : (size_t)m->num_users;
+  const float* dev = item_side ? m->V : m->U;
+  size_t b = 0, e = total;
   if (c->world > 1) {
-    b = ds->by_user.rank_begin[c->rank];
-    e = c->rank == c->world - 1 ? (size_t)m->num_users : (size_t)ds->by_user.rank_begin[c->rank + 1];
+    b = side.rank_begin[c->rank];
+    e = c->rank == c->world - 1 ? total : (size_t)side.rank_begin[c->rank + 1];
   }
   CK(cudaEventRecord(c->copy_ev, c->stream));
   CK(cudaStreamWaitEvent(c->copy_stream, c->copy_ev, 0));
   if (e > b)
-    CK(cudaMemcpyAsync(m->early_U_host + b * d, m->U + b * d, sizeof(float) * (e - b) * d, cudaMemcpyDeviceToHost,
-                       c->copy_stream));
-  m->early_U_done = true;
+    CK(cudaMemcpyAsync(host + b * d, dev + b * d, sizeof(float) * (e - b) * d, cudaMemcpyDeviceToHost, c->copy_stream));
+  done = true;
   return FRX_OK;
 }
+static int maybe_download_U(frx_model* m, frx_dataset* ds) { return maybe_download(m, ds, false); }
+static int maybe_download_V(frx_model* m, frx_dataset* ds) { return maybe_download(m, ds, true); }
 
 extern "C" int frx_model_train(frx_model* m, frx_dataset* ds) {
   frx_context* c = m->ctx;
@@ -1031,6 +1038,7 @@ extern "C" int frx_model_train(frx_model* m, frx_dataset* ds) {
       RC(stage_ials_step(m, ds, true, m->U, nullptr, nullptr));
       RC(maybe_download_U(m, ds));
       RC(stage_ials_step(m, ds, false, m->V, nullptr, nullptr));
+      RC(maybe_download_V(m, ds));
       RC(stage_item_gramian(m));  // ComputeUserLoss recomputes the Gramian, ials.h:371
       RC(stage_user_loss(m, ds, m->G, nullptr));
       break;
@@ -1047,6 +1055,7 @@ extern "C" int frx_model_train(frx_model* m, frx_dataset* ds) {
       RC(stage_step_u(m, ds));
       RC(maybe_download_U(m, ds));
       RC(stage_step_v(m, ds, m->U));
+      RC(maybe_download_V(m, ds));
       RC(stage_item_gramian(m));
       RC(stage_user_loss(m, ds, m->G, nullptr));
       RC(stage_means(m));
@@ -1068,6 +1077,7 @@ extern "C" int frx_model_train(frx_model* m, frx_dataset* ds) {
         RC(stage_step_u(m, ds));
         if (t == m->cfg.pd_iterations - 1) RC(maybe_download_U(m, ds));
         RC(stage_step_v(m, ds, m->U));
+        if (t == m->cfg.pd_iterations - 1) RC(maybe_download_V(m, ds));
         RC(stage_item_gramian(m));
         RC(stage_user_loss(m, ds, m->G, nullptr));
         RC(stage_means(m));
@@ -1100,15 +1110,16 @@ extern "C" int frx_model_train(frx_model* m, frx_dataset* ds) {
 extern "C" int frx_model_train_to_host(frx_model* m, frx_dataset* ds, float* U, float* V) {
   frx_context* c = m->ctx;
   m->early_U_host = U;
-  m->early_U_done = false;
+  m->early_V_host = V;
+  m->early_U_done = m->early_V_done = false;
   int rc = frx_model_train(m, ds);
-  const bool u_done = m->early_U_done;
-  m->early_U_host = nullptr;
-  m->early_U_done = false;
+  const bool u_done = m->early_U_done, v_done = m->early_V_done;
+  m->early_U_host = m->early_V_host = nullptr;
+  m->early_U_done = m->early_V_done = false;
   if (rc) return rc;
-  rc = frx_model_get_factors_sharded(m, ds, u_done ? nullptr : U, V);  // synchronises the main stream
+  rc = frx_model_get_factors_sharded(m, ds, u_done ? nullptr : U, v_done ? nullptr : V);  // synchronises the main stream
   if (rc) return rc;
-  if (u_done) CK(cudaStreamSynchronize(c->copy_stream));
+  if (u_done || v_done) CK(cudaStreamSynchronize(c->copy_stream));
   return FRX_OK;
 }
 
