@@ -84,6 +84,14 @@ def main():
         own_ok = (np.array_equal(Ud[ub[rank]:ub[rank + 1]], Uh[ub[rank]:ub[rank + 1]]) and
                   np.array_equal(Vd[ib[rank]:ib[rank + 1]], Vh[ib[rank]:ib[rank + 1]]) and
                   np.all(Ud[:ub[rank]] == -7.0) and np.all(Ud[ub[rank + 1]:ds.max_user + 1] == -7.0))
+        # train_to_host: the overlapped device->host copies must deliver this rank's rows of the NEW factors
+        Ut = np.full((nu, d), -7.0, np.float32)
+        Vt = np.full((ni, d), -7.0, np.float32)
+        m.train_to_host(ds, Ut, Vt)
+        U3, V3 = m.factors()
+        own_ok = (own_ok and np.array_equal(Ut[ub[rank]:ub[rank + 1]], U3[ub[rank]:ub[rank + 1]]) and
+                  np.array_equal(Vt[ib[rank]:ib[rank + 1]], V3[ib[rank]:ib[rank + 1]]) and
+                  np.all(Ut[:ub[rank]] == -7.0) and np.all(Vt[:ib[rank]] == -7.0))
         if not (np.array_equal(U2, Uh) and np.array_equal(V2, Vh) and own_ok):
             print(f"[dist_parity] rank {rank}: sharded factor transfer mismatch for {name} d={d}", flush=True)
             failures += 1
