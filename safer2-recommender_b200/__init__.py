@@ -24,7 +24,7 @@ EXPORTS = [
     "frx_model_destroy", "frx_model_init_factors", "frx_model_set_factors", "frx_model_get_factors", "frx_model_upload_factors",
     "frx_model_initialize", "frx_model_train", "frx_model_stage", "frx_model_get_state",
     "frx_model_set_state", "frx_model_compute_stats", "frx_model_last_snr", "frx_model_evaluate",
-    "frx_context_launch_count", "frx_context_set_profiling", "frx_context_stage_times", "frx_gramian",
+    "frx_context_launch_count", "frx_context_set_profiling", "frx_context_stage_times", "frx_gramian", "frx_sym_eig",
 ]
 
 
@@ -122,6 +122,7 @@ def lib():
     L.frx_context_set_profiling.argtypes = [vp, C.c_int]
     L.frx_context_stage_times.argtypes = [vp, C.c_char_p, C.c_int, fp, C.c_int]
     L.frx_gramian.argtypes = [vp, fp, C.c_int, C.c_int, fp, fp]
+    L.frx_sym_eig.argtypes = [vp, fp, C.c_int, fp, fp, ip]
     _lib = L
     return L
 
@@ -180,6 +181,16 @@ class Context:
         out = np.zeros((E.shape[1], E.shape[1]), np.float32)
         _check(lib().frx_gramian(self.h, _fp(E), E.shape[0], E.shape[1], _fp(w), _fp(out)))
         return out
+
+    def sym_eig(self, G):
+        """(Q, lam, sweeps) with G = Q diag(lam) Q^T; d = 128 or 256 (the kernel of the dual-form row path)."""
+        G = np.ascontiguousarray(G, np.float32)
+        d = G.shape[0]
+        Q = np.zeros((d, d), np.float32)
+        lam = np.zeros(d, np.float32)
+        sweeps = C.c_int(0)
+        _check(lib().frx_sym_eig(self.h, _fp(G), d, _fp(Q), _fp(lam), C.byref(sweeps)))
+        return Q, lam, sweeps.value
 
     def close(self):
         if self.h:

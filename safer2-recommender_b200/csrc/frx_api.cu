@@ -37,6 +37,8 @@ static int fail(int code, const char* fmt, ...) {
       return fail(FRX_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
+#define RC0(x) do { int rc0__ = (x); if (rc0__) return rc0__; } while (0)
+
 struct StageTimer {
   std::string name;
   cudaEvent_t a, b;
@@ -54,6 +56,9 @@ struct frx_context {
   size_t gram_ws_floats = 0;
   float* row_scratch = nullptr;
   size_t row_scratch_floats = 0;
+  float* wb_scratch = nullptr;  // rotated solutions of the dual-form row path
+  size_t wb_scratch_floats = 0;
+  int* wb_counter = nullptr;    // its work queue
   double* dws = nullptr;   // xi partials / mean partials
   int* status_dev = nullptr;
   bool profiling = false;
@@ -80,6 +85,15 @@ struct frx_context {
     row_scratch_floats = 0;
     CK(cudaMalloc(&row_scratch, floats * sizeof(float)));
     row_scratch_floats = floats;
+    return 0;
+  }
+  int ensure_wb_scratch(size_t floats) {
+    if (floats <= wb_scratch_floats) return 0;
+    if (wb_scratch) cudaFree(wb_scratch);
+    wb_scratch = nullptr;
+    wb_scratch_floats = 0;
+    CK(cudaMalloc(&wb_scratch, floats * sizeof(float)));
+    wb_scratch_floats = floats;
     return 0;
   }
   void stage_begin(const char* name) {
@@ -121,6 +135,11 @@ struct Csr {
   int* chunk_row = nullptr;
   int* chunk_off = nullptr;
   float* resid = nullptr;  // [nnz]
+  // dual-form row path: the rows of `order` with at most FRX_WB_MAX entries (its tail: order is longest first)
+  // packed into groups of four 32-entry slots (WbParams::grp_slots)
+  int num_direct = 0;      // order[0, num_direct) have more than FRX_WB_MAX entries
+  int wb_num_groups = 0;
+  int* wb_groups = nullptr;
 };
 
 struct frx_dataset {
@@ -133,8 +152,24 @@ struct frx_dataset {
   int* user_ids_dev = nullptr;
 };
 
+// Eigenbasis of a Gramian and the fixed-side factors rotated into it (dual-form row path).
+struct Basis {
+  float *Q = nullptr, *QT = nullptr, *lam = nullptr, *Et = nullptr;
+  int* info = nullptr;
+  size_t et_rows = 0;
+  bool valid = false;
+};
+
+static void free_basis(Basis& b) {
+  cudaFree(b.Q); cudaFree(b.QT); cudaFree(b.lam); cudaFree(b.Et); cudaFree(b.info);
+  b = Basis();
+}
+
 struct frx_model {
   frx_context* ctx = nullptr;
+  Basis basisV;    // of the cached item Gramian G and V (user half-steps of SAFER2 / ERM-MF, fold-in evaluation)
+  Basis basisTmp;  // of a Gramian computed inside a half-step (iALS)
+  bool G_dirty = false;  // V was overwritten from the host: G = V^T V must be recomputed before it is read
   float* early_U_host = nullptr;  // frx_model_train_to_host: where U / V go as soon as their half-step is final
   float* early_V_host = nullptr;
   bool early_U_done = false, early_V_done = false;
@@ -183,7 +218,8 @@ extern "C" int frx_context_create(int device, void* cuda_stream, frx_context** o
   }
   CK(cudaMalloc(&c->dws, sizeof(double) * (xi_partials_doubles(c->num_sms) + 512)));
   CK(cudaMalloc(&c->status_dev, sizeof(int)));
-  CK(cudaMemset(c->status_dev, 0, sizeof(int)));
+  CK(cudaMemsetAsync(c->status_dev, 0, sizeof(int), c->stream));
+  CK(cudaMalloc(&c->wb_counter, sizeof(int)));
   *out = c;
   return FRX_OK;
 }
@@ -198,6 +234,8 @@ extern "C" void frx_context_destroy(frx_context* c) {
   for (auto& t : c->timers) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   cudaFree(c->gram_ws);
   cudaFree(c->row_scratch);
+  cudaFree(c->wb_scratch);
+  cudaFree(c->wb_counter);
   cudaFree(c->dws);
   cudaFree(c->status_dev);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -209,9 +247,11 @@ extern "C" void frx_context_destroy(frx_context* c) {
 extern "C" int frx_context_sync(frx_context* c) {
   CK(cudaStreamSynchronize(c->stream));
   int st = 0;
-  CK(cudaMemcpy(&st, c->status_dev, sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpyAsync(&st, c->status_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   if (st != 0) {
-    cudaMemset(c->status_dev, 0, sizeof(int));
+    cudaMemsetAsync(c->status_dev, 0, sizeof(int), c->stream);
+    cudaStreamSynchronize(c->stream);
     return fail(FRX_ERR_NUMERIC, "non-positive Cholesky pivot (reference asserts at safer2.h:160)");
   }
   return FRX_OK;
@@ -291,6 +331,14 @@ extern "C" int frx_partition_rows(const int* ptr, int nrows, int world, int row_
   return FRX_OK;
 }
 
+// Host -> device upload of a small index array on the context stream (the kernels that read it run there;
+// the host vector must stay alive until the caller's stream synchronisation).
+static int upload_ints(frx_context* c, int** dev, const std::vector<int>& h) {
+  CK(cudaMalloc(dev, sizeof(int) * std::max<size_t>(1, h.size())));
+  if (!h.empty()) CK(cudaMemcpyAsync(*dev, h.data(), sizeof(int) * h.size(), cudaMemcpyHostToDevice, c->stream));
+  return FRX_OK;
+}
+
 static int finish_csr(frx_context* c, Csr& m, const int* cost_other_dim) {
   (void)cost_other_dim;
   m.h_ptr.resize(m.nrows + 1);
@@ -305,46 +353,61 @@ static int finish_csr(frx_context* c, Csr& m, const int* cost_other_dim) {
     if (m.h_ptr[r + 1] > m.h_ptr[r]) ++m.distinct;
   for (int r = m.rank_begin[c->rank]; r < m.rank_begin[c->rank + 1]; ++r)
     if (m.h_ptr[r + 1] > m.h_ptr[r]) order.push_back(r);
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-    return (m.h_ptr[a + 1] - m.h_ptr[a]) > (m.h_ptr[b + 1] - m.h_ptr[b]);
-  });
+  auto len = [&](int r) { return m.h_ptr[r + 1] - m.h_ptr[r]; };
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return len(a) > len(b); });
   m.num_order = (int)order.size();
-  CK(cudaMalloc(&m.order, sizeof(int) * (size_t)std::max(1, m.num_order)));
-  if (m.num_order)
-    CK(cudaMemcpy(m.order, order.data(), sizeof(int) * (size_t)m.num_order, cudaMemcpyHostToDevice));
+  RC0(upload_ints(c, &m.order, order));
   // pieces of the long rows (a popular item of ML-20M has ~70K entries: one CTA would need milliseconds)
   std::vector<int> prow, poff, p0(std::max(1, m.nrows), -1);
   for (int r : order) {
-    const int n = m.h_ptr[r + 1] - m.h_ptr[r];
+    const int n = len(r);
     if (n <= FRX_SPLIT_MIN) break;  // longest first
     ++m.num_long;
     p0[r] = (int)prow.size();
     for (int off = 0; off < n; off += FRX_PIECE) { prow.push_back(r); poff.push_back(off); }
   }
-  {
-    std::vector<int> crow, coff;
-    for (int r : order) {
-      const int n = m.h_ptr[r + 1] - m.h_ptr[r];
-      for (int off = 0; off < n; off += FRX_LOSS_CHUNK) { crow.push_back(r); coff.push_back(off); }
-    }
-    m.num_chunks = (int)crow.size();
-    if (m.num_chunks) {
-      CK(cudaMalloc(&m.chunk_row, sizeof(int) * crow.size()));
-      CK(cudaMalloc(&m.chunk_off, sizeof(int) * coff.size()));
-      CK(cudaMemcpy(m.chunk_row, crow.data(), sizeof(int) * crow.size(), cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(m.chunk_off, coff.data(), sizeof(int) * coff.size(), cudaMemcpyHostToDevice));
-      CK(cudaMalloc(&m.resid, sizeof(float) * (size_t)std::max(1, m.h_ptr[m.nrows])));
-    }
+  std::vector<int> crow, coff;
+  for (int r : order) {
+    const int n = len(r);
+    for (int off = 0; off < n; off += FRX_LOSS_CHUNK) { crow.push_back(r); coff.push_back(off); }
+  }
+  m.num_chunks = (int)crow.size();
+  if (m.num_chunks) {
+    RC0(upload_ints(c, &m.chunk_row, crow));
+    RC0(upload_ints(c, &m.chunk_off, coff));
+    CK(cudaMalloc(&m.resid, sizeof(float) * (size_t)std::max(1, m.h_ptr[m.nrows])));
   }
   m.num_pieces = (int)prow.size();
   if (m.num_pieces) {
-    CK(cudaMalloc(&m.piece_row, sizeof(int) * prow.size()));
-    CK(cudaMalloc(&m.piece_off, sizeof(int) * poff.size()));
-    CK(cudaMalloc(&m.row_piece0, sizeof(int) * p0.size()));
-    CK(cudaMemcpy(m.piece_row, prow.data(), sizeof(int) * prow.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(m.piece_off, poff.data(), sizeof(int) * poff.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(m.row_piece0, p0.data(), sizeof(int) * p0.size(), cudaMemcpyHostToDevice));
+    RC0(upload_ints(c, &m.piece_row, prow));
+    RC0(upload_ints(c, &m.piece_off, poff));
+    RC0(upload_ints(c, &m.row_piece0, p0));
   }
+  // Groups of the dual-form row path: the rows with at most FRX_WB_MAX entries take ceil(n / 32) consecutive
+  // 32-entry slots of a 4-slot group; first-fit decreasing (order is longest first), heaviest groups first.
+  m.num_direct = 0;
+  while (m.num_direct < m.num_order && len(order[m.num_direct]) > FRX_WB_MAX) ++m.num_direct;
+  std::vector<int> groups;          // [g][4]
+  std::vector<int> open_by_free[4]; // groups with 1..3 free slots
+  for (int i = m.num_direct; i < m.num_order; ++i) {
+    const int need = (len(order[i]) + 31) / 32;
+    int g = -1;
+    for (int fr = need; fr <= 3 && g < 0; ++fr)
+      if (!open_by_free[fr].empty()) { g = open_by_free[fr].back(); open_by_free[fr].pop_back(); }
+    int used = 0;
+    if (g < 0) {
+      g = (int)groups.size() / 4;
+      groups.insert(groups.end(), 4, -1);
+    } else {
+      while (used < 4 && groups[(size_t)g * 4 + used] >= 0) ++used;
+    }
+    for (int k = 0; k < need; ++k) groups[(size_t)g * 4 + used + k] = ((i - m.num_direct) << 2) | k;
+    const int fr = 4 - used - need;
+    if (fr > 0) open_by_free[fr].push_back(g);
+  }
+  m.wb_num_groups = (int)groups.size() / 4;
+  if (m.wb_num_groups) RC0(upload_ints(c, &m.wb_groups, groups));
+  CK(cudaStreamSynchronize(c->stream));  // the host vectors go out of scope
   return FRX_OK;
 }
 
@@ -394,6 +457,7 @@ extern "C" void frx_dataset_destroy(frx_dataset* d) {
     cudaFree(m->ptr); cudaFree(m->col); cudaFree(m->tup); cudaFree(m->order);
     cudaFree(m->piece_row); cudaFree(m->piece_off); cudaFree(m->row_piece0);
     cudaFree(m->chunk_row); cudaFree(m->chunk_off); cudaFree(m->resid);
+    cudaFree(m->wb_groups);
   }
   cudaFree(d->xmap);
   cudaFree(d->user_ids_dev);
@@ -426,11 +490,9 @@ static int ensure_eval_maps(frx_dataset* d) {
       xmap[r] = (int)d->h_user_ids.size();
       d->h_user_ids.push_back(r);
     }
-  CK(cudaMalloc(&d->xmap, sizeof(int) * xmap.size()));
-  CK(cudaMemcpy(d->xmap, xmap.data(), sizeof(int) * xmap.size(), cudaMemcpyHostToDevice));
-  CK(cudaMalloc(&d->user_ids_dev, sizeof(int) * std::max<size_t>(1, d->h_user_ids.size())));
-  if (!d->h_user_ids.empty())
-    CK(cudaMemcpy(d->user_ids_dev, d->h_user_ids.data(), sizeof(int) * d->h_user_ids.size(), cudaMemcpyHostToDevice));
+  RC0(upload_ints(d->ctx, &d->xmap, xmap));
+  RC0(upload_ints(d->ctx, &d->user_ids_dev, d->h_user_ids));
+  CK(cudaStreamSynchronize(d->ctx->stream));  // xmap goes out of scope
   return FRX_OK;
 }
 
@@ -518,6 +580,8 @@ static int reset_state(frx_model* m) {
   frx_context* c = m->ctx;
   int rc = gramian_into(m, m->V, m->num_items, 0, m->cfg.dim, 0, m->cfg.dim, nullptr, m->G);
   if (rc) return rc;
+  m->basisV.valid = false;
+  m->G_dirty = false;
   launch_fill(m->z, m->num_users, m->cfg.alpha, c->stream, &c->launches);
   CK(cudaMemsetAsync(m->loss, 0, sizeof(float) * m->num_users, c->stream));
   CK(cudaMemsetAsync(m->hist_size, 0, sizeof(float) * m->num_users, c->stream));
@@ -569,6 +633,8 @@ extern "C" void frx_model_destroy(frx_model* m) {
                    m->scal, m->Uprev, m->pred})
     cudaFree(p);
   cudaFree(m->snr_dev);
+  free_basis(m->basisV);
+  free_basis(m->basisTmp);
   for (int i = 0; i < 2; ++i) {
     if (m->snr_host[i]) cudaFreeHost(m->snr_host[i]);
     if (m->snr_ev[i]) cudaEventDestroy(m->snr_ev[i]);
@@ -590,6 +656,7 @@ extern "C" int frx_model_upload_factors(frx_model* m, const float* U, const floa
   const size_t d = m->cfg.dim;
   if (U) CK(cudaMemcpyAsync(m->U, U, sizeof(float) * m->num_users * d, cudaMemcpyHostToDevice, c->stream));
   if (V) CK(cudaMemcpyAsync(m->V, V, sizeof(float) * m->num_items * d, cudaMemcpyHostToDevice, c->stream));
+  if (V) m->G_dirty = true;  // item_gramian_ == V^T V is an invariant at Train() entry (safer2.h:294)
   return FRX_OK;
 }
 
@@ -643,6 +710,7 @@ extern "C" int frx_model_upload_factors_sharded(frx_model* m, frx_dataset* train
       CK(cudaMemcpyAsync(dev[k] + last * d, host[k] + last * d, sizeof(float) * (total - last) * d, cudaMemcpyHostToDevice, c->stream));
     { const int rc_ = allgather_rows(c, dev[k], d, side[k]->rank_begin); if (rc_) return rc_; }
   }
+  if (V) m->G_dirty = true;
   return FRX_OK;
 }
 
@@ -689,7 +757,41 @@ struct RowCall {
   int mode;
   int cs, bd;
   float* pred;
+  const Basis* basis = nullptr;  // eigenbasis of G with E rotated into it, or null: no dual-form path
 };
+
+// G = Q diag(lam) Q^T and Et = E * Q on the context stream.
+static int compute_basis(frx_model* m, Basis& b, const float* G, const float* E, int rows) {
+  frx_context* c = m->ctx;
+  const size_t d = m->cfg.dim;
+  if (!b.Q) {
+    CK(cudaMalloc(&b.Q, sizeof(float) * d * d));
+    CK(cudaMalloc(&b.QT, sizeof(float) * d * d));
+    CK(cudaMalloc(&b.lam, sizeof(float) * d));
+    CK(cudaMalloc(&b.info, sizeof(int)));
+  }
+  if (b.et_rows < (size_t)rows) {
+    cudaFree(b.Et);
+    b.Et = nullptr;
+    CK(cudaMalloc(&b.Et, sizeof(float) * (size_t)rows * d));
+    b.et_rows = rows;
+  }
+  c->stage_begin("eig");
+  if (launch_sym_eig(G, (int)d, b.Q, b.QT, b.lam, b.info, c->stream, &c->launches) != 0)
+    return fail(FRX_ERR_CUDA, "launch of jacobi_eig_kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+  c->stage_end();
+  c->stage_begin("rotate");
+  launch_rows_gemm(E, rows, (int)d, b.Q, b.Et, nullptr, nullptr, c->stream, &c->launches);
+  c->stage_end();
+  CK(cudaGetLastError());
+  b.valid = true;
+  return FRX_OK;
+}
+
+static bool wb_enabled(const frx_model* m) {
+  static const bool off = getenv("FRX_DISABLE_WB") != nullptr || getenv("FRX_DISABLE_TC") != nullptr;
+  return !off && sym_eig_supported(m->cfg.dim);
+}
 
 static int run_rows(frx_model* m, const RowCall& rc_) {
   frx_context* c = m->ctx;
@@ -715,6 +817,10 @@ static int run_rows(frx_model* m, const RowCall& rc_) {
       p.dbg = dbg;
     }
     static const bool no_split = getenv("FRX_NO_SPLIT") != nullptr;
+    // rows with at most FRX_WB_MAX entries go to the dual-form kernel when the eigenbasis of G is at hand
+    const bool use_wb = rc_.basis && rc_.basis->valid && rc_.rows->wb_num_groups > 0 && row_solve_wb_supported(p);
+    const int direct_rows = use_wb ? rc_.rows->num_direct : rc_.rows->num_order;
+    p.num_rows = direct_rows;
     if (rc_.rows->num_pieces > 0 && !no_split) {
       // first launch: partial sums of the pieces of the long rows
       p.piece_stride = row_solve_tc_piece_floats(p.d);
@@ -734,10 +840,30 @@ static int run_rows(frx_model* m, const RowCall& rc_) {
       // the ordinary rows follow
       p.piece_mode = 0;
       p.order = rc_.rows->order + rc_.rows->num_long;
-      p.num_rows = rc_.rows->num_order - rc_.rows->num_long;
+      p.num_rows = direct_rows - rc_.rows->num_long;
     }
     launch_row_solve_tc(p, c->stream, c->num_sms, &c->launches);
     CK(cudaGetLastError());
+    if (use_wb) {
+      const int nwb = rc_.rows->num_order - rc_.rows->num_direct;
+      int r = c->ensure_wb_scratch((size_t)nwb * p.d);
+      if (r) return r;
+      WbParams q;
+      q.grp_slots = rc_.rows->wb_groups;
+      q.wb_rows = rc_.rows->order + rc_.rows->num_direct;
+      q.num_groups = rc_.rows->wb_num_groups;
+      q.Et = rc_.basis->Et;
+      q.lam = rc_.basis->lam;
+      q.Xt = c->wb_scratch;
+      q.counter = c->wb_counter;
+      p.order = rc_.rows->order;
+      p.num_rows = rc_.rows->num_order;
+      launch_row_solve_wb(p, q, c->stream, c->num_sms, &c->launches);
+      CK(cudaGetLastError());
+      // back to the original basis: X[row] = xt * Q^T
+      launch_rows_gemm(c->wb_scratch, nwb, p.d, rc_.basis->QT, p.X, q.wb_rows, p.xmap, c->stream, &c->launches);
+      CK(cudaGetLastError());
+    }
     if (tc_debug) {
       unsigned long long h[16];
       CK(cudaMemcpyAsync(h, dbg, sizeof h, cudaMemcpyDeviceToHost, c->stream));
@@ -781,7 +907,23 @@ static int stage_item_gramian(frx_model* m) {
   m->ctx->stage_begin("gramian_V");
   int rc = gramian_into(m, m->V, m->num_items, 0, m->cfg.dim, 0, m->cfg.dim, nullptr, m->G);
   m->ctx->stage_end();
+  m->basisV.valid = false;
+  m->G_dirty = false;
   return rc;
+}
+
+// The cached item Gramian follows V when V was overwritten from the host (frx_model_upload_factors*).
+static int refresh_item_gramian(frx_model* m) {
+  if (!m->G_dirty) return FRX_OK;
+  return stage_item_gramian(m);
+}
+
+// Eigenbasis of the cached item Gramian + V rotated into it, for the dual-form path of the user half-steps.
+static const Basis* item_basis(frx_model* m, int* rc) {
+  *rc = FRX_OK;
+  if (!wb_enabled(m)) return nullptr;
+  if (!m->basisV.valid) *rc = compute_basis(m, m->basisV, m->G, m->V, m->num_items);
+  return *rc ? nullptr : &m->basisV;
 }
 
 static int stage_user_loss(frx_model* m, frx_dataset* ds, const float* G, const float* pred) {
@@ -895,9 +1037,16 @@ static int stage_xi_exact(frx_model* m) {
 
 // StepU of SAFER2 / ERM-MF (safer2.h:437-490) on the model's own users.
 static int stage_step_u(frx_model* m, frx_dataset* ds) {
+  const Basis* basis = nullptr;
+  if (m->cfg.model != FRX_CVAR_MF && ds->by_user.wb_num_groups > 0) {
+    int brc;
+    basis = item_basis(m, &brc);
+    if (brc) return brc;
+  }
   m->ctx->stage_begin("step_U");
   RowCall rc{&ds->by_user, m->V, m->num_items, m->U, nullptr, nullptr, m->G, nullptr, m->z,
              RM_SAFER_U, 0, m->cfg.dim, nullptr};
+  rc.basis = basis;
   if (m->cfg.model == FRX_CVAR_MF) rc.mode = RM_CVAR_U;
   int r = run_rows_sharded(m, rc);
   m->ctx->stage_end();
@@ -931,9 +1080,16 @@ static int stage_ials_step(frx_model* m, frx_dataset* ds, bool user_side, float*
   int r = gramian_into(m, other, n_other, 0, m->cfg.dim, 0, m->cfg.dim, nullptr, m->Gz);
   c->stage_end();
   if (r) return r;
-  c->stage_begin(user_side ? "step_U" : "step_V");
   const Csr* rows = rows_override ? rows_override : (user_side ? &ds->by_user : &ds->by_item);
+  const Basis* basis = nullptr;
+  if (wb_enabled(m) && rows->wb_num_groups > 0) {
+    r = compute_basis(m, m->basisTmp, m->Gz, other, n_other);
+    if (r) return r;
+    basis = &m->basisTmp;
+  }
+  c->stage_begin(user_side ? "step_U" : "step_V");
   RowCall rc{rows, other, n_other, X, nullptr, xmap, m->Gz, nullptr, nullptr, RM_IALS, 0, m->cfg.dim, nullptr};
+  rc.basis = basis;
   r = run_rows_sharded(m, rc);
   c->stage_end();
   return r;
@@ -979,6 +1135,7 @@ extern "C" int frx_model_initialize(frx_model* m, frx_dataset* ds) {
   if (m->is_ials_family()) return FRX_OK;  // run_model.cc:246-257
   if (ds->by_user.nrows > m->num_users || ds->by_item.nrows > m->num_items)
     return fail(FRX_ERR_ARG, "dataset ids exceed the model's num_users/num_items");
+  RC(refresh_item_gramian(m));
   const float* pred = nullptr;
   if (m->cfg.model == FRX_SAFER2PP) {
     RC(ensure_pred(m, ds->num_tuples));
@@ -1030,6 +1187,7 @@ extern "C" int frx_model_train(frx_model* m, frx_dataset* ds) {
   if (ds->by_user.nrows > m->num_users || ds->by_item.nrows > m->num_items)
     return fail(FRX_ERR_ARG, "dataset ids exceed the model's num_users/num_items");
   c->timers_used = 0;
+  RC(refresh_item_gramian(m));
   const int d = m->cfg.dim, B = m->cfg.block_size;
   if (c->world > 1 && m->is_pp())
     return fail(FRX_ERR_ARG, "iALS++ / SAFER2++ are single-GPU in this build (the tuple-indexed prediction cache is not sharded)");
@@ -1126,6 +1284,7 @@ extern "C" int frx_model_train_to_host(frx_model* m, frx_dataset* ds, float* U, 
 extern "C" int frx_model_stage(frx_model* m, frx_dataset* ds, int stage) {
   frx_context* c = m->ctx;
   CK(cudaSetDevice(c->device));
+  RC(refresh_item_gramian(m));
   const int d = m->cfg.dim;
   switch (stage) {
     case 0: return stage_weights(m);
@@ -1153,6 +1312,7 @@ extern "C" int frx_model_get_state(frx_model* m, float* z, float* loss, float* h
   frx_context* c = m->ctx;
   CK(cudaSetDevice(c->device));
   const size_t d = m->cfg.dim;
+  if (gramian) RC(refresh_item_gramian(m));
   if (scalars) RC(stage_means(m));
   if (z) CK(cudaMemcpyAsync(z, m->z, sizeof(float) * m->num_users, cudaMemcpyDeviceToHost, c->stream));
   if (loss) CK(cudaMemcpyAsync(loss, m->loss, sizeof(float) * m->num_users, cudaMemcpyDeviceToHost, c->stream));
@@ -1235,6 +1395,8 @@ extern "C" int frx_model_load(frx_model* m, const char* path) {
   }
   int rc = gramian_into(m, m->V, m->num_items, 0, m->cfg.dim, 0, m->cfg.dim, nullptr, m->G);
   if (rc) return rc;
+  m->basisV.valid = false;
+  m->G_dirty = false;
   m->xi_calls = hdr[4];
   CK(cudaStreamSynchronize(c->stream));  // buf goes out of scope
   return FRX_OK;
@@ -1334,6 +1496,7 @@ extern "C" int frx_model_evaluate(frx_model* m, frx_dataset* tr, frx_dataset* te
   if (!recall) return nu;
   if (c->world > 1) return fail(FRX_ERR_ARG, "evaluate: run on a single-rank context");
   if (tr->by_item.nrows > m->num_items) return fail(FRX_ERR_ARG, "test items exceed the model's num_items");
+  RC(refresh_item_gramian(m));
   const int d = m->cfg.dim, B = m->cfg.block_size;
   int max_k = 0;
   for (int i = 0; i < nk; ++i) max_k = std::max(max_k, k_list[i]);
@@ -1350,6 +1513,11 @@ extern "C" int frx_model_evaluate(frx_model* m, frx_dataset* tr, frx_dataset* te
     case FRX_SAFER2: {  // safer2.h:246-252: StepU with weight 1 and the cached item_gramian_
       RowCall rc{&tr->by_user, m->V, m->num_items, Ut, nullptr, tr->xmap, m->G, nullptr, nullptr,
                  RM_SAFER_U, 0, d, nullptr};
+      if (tr->by_user.wb_num_groups > 0) {
+        int brc;
+        rc.basis = item_basis(m, &brc);
+        RC(brc);
+      }
       RC(run_rows(m, rc));
       break;
     }
@@ -1432,5 +1600,31 @@ extern "C" int frx_gramian(frx_context* c, const float* E, int n, int d, const f
   CK(cudaMemcpyAsync(out, dG, sizeof(float) * (size_t)d * d, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   cudaFree(dE); cudaFree(dw); cudaFree(dG);
+  return FRX_OK;
+}
+
+// G = Q diag(lam) Q^T of a symmetric d x d matrix (d = 128 / 256) with the cluster Jacobi kernel; host in / out.
+// Q is row-major with eigenvector i in column i.  *sweeps < 0: not converged.
+extern "C" int frx_sym_eig(frx_context* c, const float* G, int d, float* Q, float* lam, int* sweeps) {
+  CK(cudaSetDevice(c->device));
+  if (!sym_eig_supported(d)) return fail(FRX_ERR_ARG, "frx_sym_eig: d must be 128 or 256");
+  float *dG = nullptr, *dQ = nullptr, *dQT = nullptr, *dl = nullptr;
+  int* dinfo = nullptr;
+  const size_t dd = (size_t)d * d;
+  CK(cudaMalloc(&dG, sizeof(float) * dd));
+  CK(cudaMalloc(&dQ, sizeof(float) * dd));
+  CK(cudaMalloc(&dQT, sizeof(float) * dd));
+  CK(cudaMalloc(&dl, sizeof(float) * d));
+  CK(cudaMalloc(&dinfo, sizeof(int)));
+  CK(cudaMemcpyAsync(dG, G, sizeof(float) * dd, cudaMemcpyHostToDevice, c->stream));
+  const int rc = launch_sym_eig(dG, d, dQ, dQT, dl, dinfo, c->stream, &c->launches);
+  if (rc == 0) {
+    CK(cudaMemcpyAsync(Q, dQ, sizeof(float) * dd, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(lam, dl, sizeof(float) * d, cudaMemcpyDeviceToHost, c->stream));
+    if (sweeps) CK(cudaMemcpyAsync(sweeps, dinfo, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(dG); cudaFree(dQ); cudaFree(dQT); cudaFree(dl); cudaFree(dinfo);
+  if (rc) return fail(FRX_ERR_CUDA, "launch of jacobi_eig_kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
   return FRX_OK;
 }

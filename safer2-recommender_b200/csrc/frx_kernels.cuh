@@ -73,6 +73,31 @@ int row_solve_generic_grid(int num_rows, int num_sms);
 bool row_solve_tc_supported(const RowParams& p);
 void launch_row_solve_tc(const RowParams& p, cudaStream_t s, int num_sms, long long* launches);
 
+// Dual-form row path (frx_row_wb.cu) for rows with at most FRX_WB_MAX entries: needs the eigenbasis of the
+// Gramian (frx_eig.cu) and the fixed-side factors rotated into it (frx_gemm.cu).
+constexpr int FRX_WB_MAX = 128;
+struct WbParams {
+  const int* grp_slots;  // [num_groups][4]: (index into wb_rows << 2) | 32-entry chunk of that row, or -1
+  const int* wb_rows;    // row ids solved by this path
+  int num_groups;
+  const float* Et;       // [num_other x d] = E * Q
+  const float* lam;      // [d] eigenvalues of G
+  float* Xt;             // [num wb rows x d] rotated solutions (the caller applies Q^T)
+  int* counter;          // work queue (zeroed by the launcher)
+};
+bool row_solve_wb_supported(const RowParams& p);
+void launch_row_solve_wb(const RowParams& p, const WbParams& q, cudaStream_t s, int num_sms, long long* launches);
+
+// G = Q diag(lam) Q^T for the symmetric d x d Gramian (d = 128 / 256): Q row-major (column i = eigenvector i),
+// QT = Q^T, all fp32; info[0] = sweeps (negative: not converged).  Returns 0 on success.
+bool sym_eig_supported(int d);
+int launch_sym_eig(const float* G, int d, float* Q, float* QT, float* lam, int* info, cudaStream_t s,
+                   long long* launches);
+
+// C[out(i)][:] = A[i][:] * B, A [M x d], B [d x d] row-major, out(i) = c_map[c_rows[i]] (either may be null).
+void launch_rows_gemm(const float* A, int M, int d, const float* B, float* C, const int* c_rows, const int* c_map,
+                      cudaStream_t s, long long* launches);
+
 // out[bd x fd] = sum_r w[r] * E[r][cs+i] * E[r][fs+j]; two-stage, deterministic.
 void launch_gramian(const float* E, int n, int d, int cs, int bd, int fs, int fd, const float* w,
                     float* out, int ld_out, float* workspace, size_t workspace_floats,

@@ -289,6 +289,55 @@ def test_tensor_core_row_kernel_epoch(pkg, O, ctx, name, cfg, d):
     ds.close()
 
 
+@pytest.mark.parametrize("d", [128, 256])
+def test_sym_eig_of_a_gramian(ctx, d):
+    """The cluster Jacobi kernel behind the dual-form row path: G = Q diag(lam) Q^T to fp32 accuracy, Q
+    orthogonal, eigenvalues equal to LAPACK's (fp64) on a Gramian with a decaying spectrum."""
+    rng = np.random.default_rng(d)
+    E = (rng.standard_normal((3000, d)) * np.exp(-np.arange(d) / 40.0)[None, :]) @ np.linalg.qr(rng.standard_normal((d, d)))[0]
+    G = (E.T @ E).astype(np.float32)
+    Q, lam, sweeps = ctx.sym_eig(G)
+    print("jacobi sweeps", sweeps)
+    assert 0 < sweeps < 30
+    G64 = 0.5 * (G.astype(np.float64) + G.astype(np.float64).T)
+    Q64 = Q.astype(np.float64)
+    scale = np.abs(G64).max()
+    assert np.abs(Q64.T @ Q64 - np.eye(d)).max() < 5e-6
+    assert np.abs(Q64 @ np.diag(lam.astype(np.float64)) @ Q64.T - G64).max() / scale < 5e-6
+    w = np.linalg.eigvalsh(G64)
+    assert np.abs(np.sort(lam.astype(np.float64)) - w).max() / w.max() < 1e-6
+
+
+@pytest.mark.parametrize("d", [128, 256])
+@pytest.mark.parametrize("name,cfg", [
+    ("ials", dict(uobs_weight=0.1, reg=0.003)),
+    ("safer2", dict(uobs_weight=0.002, reg=0.002, bandwidth=0.18)),
+])
+def test_dual_form_rows_match_the_oracle(pkg, O, ctx, name, cfg, d):
+    """Rows with at most 128 entries take the dual-form kernel (n x n system in the eigenbasis of the Gramian,
+    rows packed four 32-entry slots to a group).  Histories 1..128 cover every slot count and the packing of
+    1 + 3, 2 + 2, 2 + 1 + 1 and 1 + 1 + 1 + 1 slots; after three epochs (trained factors, wider spectrum of G)
+    every row must still agree with the fp32 oracle."""
+    nu, ni = 900, 700
+    heavy = [(i, n) for i, n in enumerate([1, 2, 31, 32, 33, 63, 64, 65, 95, 96, 97, 127, 128, 129, 160, 300])]
+    users, items = helpers.synth_tuples(nu, ni, 40, seed=91, heavy_rows=heavy, empty_users=(20,), empty_items=(5,))
+    ods, om, ds, m = make_pair(pkg, O, ctx, users, items, nu, ni, model=name, dim=d, **cfg)
+    om.initialize(ods)
+    m.initialize(ds)
+    for epoch in range(3):
+        om.train(ods)
+        m.train(ds)
+        U, V = m.factors()
+        Uo, Vo = om.factors()
+        rowerr = np.linalg.norm(U - Uo, axis=1) / np.maximum(np.linalg.norm(Uo, axis=1), 1e-12)
+        print(name, d, "epoch", epoch, "U", rel_fro(U, Uo), "V", rel_fro(V, Vo), "worst user row", int(rowerr.argmax()), float(rowerr.max()))
+        assert rel_fro(U, Uo) < FACTOR_TOL * (epoch + 1), rel_fro(U, Uo)
+        assert rel_fro(V, Vo) < FACTOR_TOL * (epoch + 1), rel_fro(V, Vo)
+        assert rowerr.max() < 1e-3 * (epoch + 1), (int(rowerr.argmax()), float(rowerr.max()))
+    m.close()
+    ds.close()
+
+
 @pytest.mark.parametrize("name,cfg,d,long_side", [
     ("safer2", dict(uobs_weight=0.05, reg=0.05, bandwidth=0.15), 128, "item"),
     ("ials", dict(uobs_weight=0.1, reg=0.05), 256, "item"),
