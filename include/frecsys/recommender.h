@@ -87,6 +87,9 @@ public:
     if (print_trainstats_ && !stats_after_train()) PrintLosses(ds);  // safer2.h:267 (before the update)
     check(frx_model_train(model_, ds), "frx_model_train");
     if (print_trainstats_ && stats_after_train()) PrintLosses(ds);   // ials.h:203 (after both steps)
+    // the reference's Train() is synchronous: the epoch is complete (and a non-positive pivot has been
+    // reported, safer2.h:160) when it returns, so `Timer: Train=` in run_model measures the whole epoch
+    check(frx_context_sync(ctx_), "frx_model_train");
     after_train();
   }
 

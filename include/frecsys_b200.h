@@ -165,11 +165,11 @@ int frx_context_set_profiling(frx_context* ctx, int on);
 int frx_context_stage_times(frx_context* ctx, char* names_buf, int buf_len, float* ms, int max_n);
 /* Standalone Gramian G = E^T diag(w) E for tests / microbenchmarks (host in/out). */
 int frx_gramian(frx_context* ctx, const float* E, int n, int d, const float* w, float* out);
-/* Standalone symmetric eigendecomposition G = Q diag(lam) Q^T (d = 128 or 256; host in/out) with the kernel
- * the dual-form row path uses on the Gramian: Q row-major [d x d], eigenvector i in column i; lam[d];
- * *sweeps = Jacobi sweeps taken (negative: not converged).  Replaces nothing in the reference (it has no
- * eigen-solver): the dual form solves the same systems as Eigen::LLT in safer2.h:159-161 / ials.h:140-142. */
-int frx_sym_eig(frx_context* ctx, const float* G, int d, float* Q, float* lam, int* sweeps);
+/* Standalone tridiagonal reduction G = H T H^T (d = 128 or 256; host in/out) with the kernel the dual-form row
+ * path runs on the Gramian: H row-major [d x d] orthogonal, tdiag[d] = diag(T), tsub[d] with tsub[j] = T[j][j-1]
+ * (tsub[0] = 0).  Replaces nothing in the reference (it has no such step): the dual form solves the same
+ * systems as Eigen::LLT in safer2.h:159-161 / ials.h:140-142. */
+int frx_sym_tridiag(frx_context* ctx, const float* G, int d, float* H, float* tdiag, float* tsub);
 
 #ifdef __cplusplus
 }

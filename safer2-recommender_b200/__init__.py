@@ -24,7 +24,7 @@ EXPORTS = [
     "frx_model_destroy", "frx_model_init_factors", "frx_model_set_factors", "frx_model_get_factors", "frx_model_upload_factors",
     "frx_model_initialize", "frx_model_train", "frx_model_stage", "frx_model_get_state",
     "frx_model_set_state", "frx_model_compute_stats", "frx_model_last_snr", "frx_model_evaluate",
-    "frx_context_launch_count", "frx_context_set_profiling", "frx_context_stage_times", "frx_gramian", "frx_sym_eig",
+    "frx_context_launch_count", "frx_context_set_profiling", "frx_context_stage_times", "frx_gramian", "frx_sym_tridiag",
 ]
 
 
@@ -122,7 +122,7 @@ def lib():
     L.frx_context_set_profiling.argtypes = [vp, C.c_int]
     L.frx_context_stage_times.argtypes = [vp, C.c_char_p, C.c_int, fp, C.c_int]
     L.frx_gramian.argtypes = [vp, fp, C.c_int, C.c_int, fp, fp]
-    L.frx_sym_eig.argtypes = [vp, fp, C.c_int, fp, fp, ip]
+    L.frx_sym_tridiag.argtypes = [vp, fp, C.c_int, fp, fp, fp]
     _lib = L
     return L
 
@@ -182,15 +182,16 @@ class Context:
         _check(lib().frx_gramian(self.h, _fp(E), E.shape[0], E.shape[1], _fp(w), _fp(out)))
         return out
 
-    def sym_eig(self, G):
-        """(Q, lam, sweeps) with G = Q diag(lam) Q^T; d = 128 or 256 (the kernel of the dual-form row path)."""
+    def sym_tridiag(self, G):
+        """(H, tdiag, tsub) with G = H T H^T, T tridiagonal (tsub[j] = T[j][j-1]); d = 128 or 256 (the kernel of
+        the dual-form row path)."""
         G = np.ascontiguousarray(G, np.float32)
         d = G.shape[0]
-        Q = np.zeros((d, d), np.float32)
-        lam = np.zeros(d, np.float32)
-        sweeps = C.c_int(0)
-        _check(lib().frx_sym_eig(self.h, _fp(G), d, _fp(Q), _fp(lam), C.byref(sweeps)))
-        return Q, lam, sweeps.value
+        H = np.zeros((d, d), np.float32)
+        td = np.zeros(d, np.float32)
+        ts = np.zeros(d, np.float32)
+        _check(lib().frx_sym_tridiag(self.h, _fp(G), d, _fp(H), _fp(td), _fp(ts)))
+        return H, td, ts
 
     def close(self):
         if self.h:

@@ -58,7 +58,7 @@ struct frx_context {
   size_t row_scratch_floats = 0;
   float* wb_scratch = nullptr;  // rotated solutions of the dual-form row path
   size_t wb_scratch_floats = 0;
-  int* wb_counter = nullptr;    // its work queue
+  int* wb_counter = nullptr;    // its work queue ([0]) and those of the direct row-kernel launches ([1..3])
   double* dws = nullptr;   // xi partials / mean partials
   int* status_dev = nullptr;
   bool profiling = false;
@@ -152,16 +152,15 @@ struct frx_dataset {
   int* user_ids_dev = nullptr;
 };
 
-// Eigenbasis of a Gramian and the fixed-side factors rotated into it (dual-form row path).
+// Tridiagonal form G = H T H^T of a Gramian and the fixed-side factors rotated into that basis (dual-form row path).
 struct Basis {
-  float *Q = nullptr, *QT = nullptr, *lam = nullptr, *Et = nullptr;
-  int* info = nullptr;
+  float *H = nullptr, *HT = nullptr, *tdiag = nullptr, *tsub = nullptr, *Et = nullptr;
   size_t et_rows = 0;
   bool valid = false;
 };
 
 static void free_basis(Basis& b) {
-  cudaFree(b.Q); cudaFree(b.QT); cudaFree(b.lam); cudaFree(b.Et); cudaFree(b.info);
+  cudaFree(b.H); cudaFree(b.HT); cudaFree(b.tdiag); cudaFree(b.tsub); cudaFree(b.Et);
   b = Basis();
 }
 
@@ -219,7 +218,7 @@ extern "C" int frx_context_create(int device, void* cuda_stream, frx_context** o
   CK(cudaMalloc(&c->dws, sizeof(double) * (xi_partials_doubles(c->num_sms) + 512)));
   CK(cudaMalloc(&c->status_dev, sizeof(int)));
   CK(cudaMemsetAsync(c->status_dev, 0, sizeof(int), c->stream));
-  CK(cudaMalloc(&c->wb_counter, sizeof(int)));
+  CK(cudaMalloc(&c->wb_counter, 4 * sizeof(int)));
   *out = c;
   return FRX_OK;
 }
@@ -760,15 +759,15 @@ struct RowCall {
   const Basis* basis = nullptr;  // eigenbasis of G with E rotated into it, or null: no dual-form path
 };
 
-// G = Q diag(lam) Q^T and Et = E * Q on the context stream.
+// G = H T H^T and Et = E * H on the context stream.
 static int compute_basis(frx_model* m, Basis& b, const float* G, const float* E, int rows) {
   frx_context* c = m->ctx;
   const size_t d = m->cfg.dim;
-  if (!b.Q) {
-    CK(cudaMalloc(&b.Q, sizeof(float) * d * d));
-    CK(cudaMalloc(&b.QT, sizeof(float) * d * d));
-    CK(cudaMalloc(&b.lam, sizeof(float) * d));
-    CK(cudaMalloc(&b.info, sizeof(int)));
+  if (!b.H) {
+    CK(cudaMalloc(&b.H, sizeof(float) * d * d));
+    CK(cudaMalloc(&b.HT, sizeof(float) * d * d));
+    CK(cudaMalloc(&b.tdiag, sizeof(float) * d));
+    CK(cudaMalloc(&b.tsub, sizeof(float) * d));
   }
   if (b.et_rows < (size_t)rows) {
     cudaFree(b.Et);
@@ -776,12 +775,12 @@ static int compute_basis(frx_model* m, Basis& b, const float* G, const float* E,
     CK(cudaMalloc(&b.Et, sizeof(float) * (size_t)rows * d));
     b.et_rows = rows;
   }
-  c->stage_begin("eig");
-  if (launch_sym_eig(G, (int)d, b.Q, b.QT, b.lam, b.info, c->stream, &c->launches) != 0)
-    return fail(FRX_ERR_CUDA, "launch of jacobi_eig_kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+  c->stage_begin("tridiag");
+  if (launch_sym_tridiag(G, (int)d, b.H, b.HT, b.tdiag, b.tsub, c->stream, &c->launches) != 0)
+    return fail(FRX_ERR_CUDA, "launch of sym_tridiag_kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
   c->stage_end();
   c->stage_begin("rotate");
-  launch_rows_gemm(E, rows, (int)d, b.Q, b.Et, nullptr, nullptr, c->stream, &c->launches);
+  launch_rows_gemm(E, rows, (int)d, b.H, b.Et, nullptr, nullptr, c->stream, &c->launches);
   c->stage_end();
   CK(cudaGetLastError());
   b.valid = true;
@@ -790,7 +789,7 @@ static int compute_basis(frx_model* m, Basis& b, const float* G, const float* E,
 
 static bool wb_enabled(const frx_model* m) {
   static const bool off = getenv("FRX_DISABLE_WB") != nullptr || getenv("FRX_DISABLE_TC") != nullptr;
-  return !off && sym_eig_supported(m->cfg.dim);
+  return !off && sym_tridiag_supported(m->cfg.dim);
 }
 
 static int run_rows(frx_model* m, const RowCall& rc_) {
@@ -830,11 +829,13 @@ static int run_rows(frx_model* m, const RowCall& rc_) {
       p.piece_row = rc_.rows->piece_row; p.piece_off = rc_.rows->piece_off; p.row_piece0 = rc_.rows->row_piece0;
       p.num_pieces = rc_.rows->num_pieces;
       p.piece_mode = 1;
+      p.work_counter = c->wb_counter + 1;
       launch_row_solve_tc(p, c->stream, c->num_sms, &c->launches);
       CK(cudaGetLastError());
       // second launch: the long rows, each started from the sum of its pieces
       p.piece_mode = 2;
       p.num_rows = rc_.rows->num_long;
+      p.work_counter = c->wb_counter + 2;
       launch_row_solve_tc(p, c->stream, c->num_sms, &c->launches);
       CK(cudaGetLastError());
       // the ordinary rows follow
@@ -842,26 +843,40 @@ static int run_rows(frx_model* m, const RowCall& rc_) {
       p.order = rc_.rows->order + rc_.rows->num_long;
       p.num_rows = direct_rows - rc_.rows->num_long;
     }
+    p.work_counter = c->wb_counter + 3;
     launch_row_solve_tc(p, c->stream, c->num_sms, &c->launches);
     CK(cudaGetLastError());
     if (use_wb) {
       const int nwb = rc_.rows->num_order - rc_.rows->num_direct;
-      int r = c->ensure_wb_scratch((size_t)nwb * p.d);
+      int r = c->ensure_wb_scratch((size_t)3 * nwb * p.d);
       if (r) return r;
       WbParams q;
       q.grp_slots = rc_.rows->wb_groups;
       q.wb_rows = rc_.rows->order + rc_.rows->num_direct;
       q.num_groups = rc_.rows->wb_num_groups;
       q.Et = rc_.basis->Et;
-      q.lam = rc_.basis->lam;
+      q.tdiag = rc_.basis->tdiag;
+      q.tsub = rc_.basis->tsub;
       q.Xt = c->wb_scratch;
+      q.lsub = c->wb_scratch + (size_t)nwb * p.d;
+      q.rsd = c->wb_scratch + (size_t)2 * nwb * p.d;
       q.counter = c->wb_counter;
       p.order = rc_.rows->order;
       p.num_rows = rc_.rows->num_order;
-      launch_row_solve_wb(p, q, c->stream, c->num_sms, &c->launches);
+      if (tc_debug) CK(cudaMemsetAsync(dbg, 0, 16 * sizeof(unsigned long long), c->stream));
+      launch_row_solve_wb(p, q, nwb, c->stream, c->num_sms, &c->launches);
       CK(cudaGetLastError());
-      // back to the original basis: X[row] = xt * Q^T
-      launch_rows_gemm(c->wb_scratch, nwb, p.d, rc_.basis->QT, p.X, q.wb_rows, p.xmap, c->stream, &c->launches);
+      if (tc_debug) {
+        unsigned long long h[16];
+        CK(cudaMemcpyAsync(h, dbg, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        const double g = (double)q.num_groups;
+        fprintf(stderr, "[frx wb] mode=%d groups=%d rows=%d | cycles/group (summed over SMs): solver set0: wait=%.0f chol=%.0f backsub=%.0f gather+sweeps=%.0f (x3 sets) | mma warp: wait_slot=%.0f wait_stage=%.0f issue=%.0f ring=%.0f\n",
+                p.mode, q.num_groups, nwb, 3 * h[0] / g, 3 * h[1] / g, 3 * h[2] / g, 3 * h[3] / g, h[4] / g, h[5] / g, h[6] / g, h[7] / g);
+        CK(cudaMemsetAsync(dbg, 0, 16 * sizeof(unsigned long long), c->stream));
+      }
+      // back to the original basis: X[row] = xt * H^T
+      launch_rows_gemm(c->wb_scratch, nwb, p.d, rc_.basis->HT, p.X, q.wb_rows, p.xmap, c->stream, &c->launches);
       CK(cudaGetLastError());
     }
     if (tc_debug) {
@@ -1603,28 +1618,26 @@ extern "C" int frx_gramian(frx_context* c, const float* E, int n, int d, const f
   return FRX_OK;
 }
 
-// G = Q diag(lam) Q^T of a symmetric d x d matrix (d = 128 / 256) with the cluster Jacobi kernel; host in / out.
-// Q is row-major with eigenvector i in column i.  *sweeps < 0: not converged.
-extern "C" int frx_sym_eig(frx_context* c, const float* G, int d, float* Q, float* lam, int* sweeps) {
+// G = H T H^T of a symmetric d x d matrix (d = 128 / 256) with the cluster Householder kernel; host in / out.
+extern "C" int frx_sym_tridiag(frx_context* c, const float* G, int d, float* H, float* tdiag, float* tsub) {
   CK(cudaSetDevice(c->device));
-  if (!sym_eig_supported(d)) return fail(FRX_ERR_ARG, "frx_sym_eig: d must be 128 or 256");
-  float *dG = nullptr, *dQ = nullptr, *dQT = nullptr, *dl = nullptr;
-  int* dinfo = nullptr;
-  const size_t dd = (size_t)d * d;
-  CK(cudaMalloc(&dG, sizeof(float) * dd));
-  CK(cudaMalloc(&dQ, sizeof(float) * dd));
-  CK(cudaMalloc(&dQT, sizeof(float) * dd));
-  CK(cudaMalloc(&dl, sizeof(float) * d));
-  CK(cudaMalloc(&dinfo, sizeof(int)));
-  CK(cudaMemcpyAsync(dG, G, sizeof(float) * dd, cudaMemcpyHostToDevice, c->stream));
-  const int rc = launch_sym_eig(dG, d, dQ, dQT, dl, dinfo, c->stream, &c->launches);
+  if (!sym_tridiag_supported(d)) return fail(FRX_ERR_ARG, "frx_sym_tridiag: d must be 128 or 256");
+  float *dG = nullptr, *dH = nullptr, *dHT = nullptr, *dd = nullptr, *ds = nullptr;
+  const size_t n2 = (size_t)d * d;
+  CK(cudaMalloc(&dG, sizeof(float) * n2));
+  CK(cudaMalloc(&dH, sizeof(float) * n2));
+  CK(cudaMalloc(&dHT, sizeof(float) * n2));
+  CK(cudaMalloc(&dd, sizeof(float) * d));
+  CK(cudaMalloc(&ds, sizeof(float) * d));
+  CK(cudaMemcpyAsync(dG, G, sizeof(float) * n2, cudaMemcpyHostToDevice, c->stream));
+  const int rc = launch_sym_tridiag(dG, d, dH, dHT, dd, ds, c->stream, &c->launches);
   if (rc == 0) {
-    CK(cudaMemcpyAsync(Q, dQ, sizeof(float) * dd, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(lam, dl, sizeof(float) * d, cudaMemcpyDeviceToHost, c->stream));
-    if (sweeps) CK(cudaMemcpyAsync(sweeps, dinfo, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(H, dH, sizeof(float) * n2, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(tdiag, dd, sizeof(float) * d, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(tsub, ds, sizeof(float) * d, cudaMemcpyDeviceToHost, c->stream));
   }
   CK(cudaStreamSynchronize(c->stream));
-  cudaFree(dG); cudaFree(dQ); cudaFree(dQT); cudaFree(dl); cudaFree(dinfo);
-  if (rc) return fail(FRX_ERR_CUDA, "launch of jacobi_eig_kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+  cudaFree(dG); cudaFree(dH); cudaFree(dHT); cudaFree(dd); cudaFree(ds);
+  if (rc) return fail(FRX_ERR_CUDA, "launch of sym_tridiag_kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
   return FRX_OK;
 }

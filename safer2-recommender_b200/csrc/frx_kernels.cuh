@@ -48,6 +48,7 @@ struct RowParams {
   size_t scratch_stride;
   int use_smem_matrix;
   int* status;  // set non-zero on a non-positive pivot
+  int* work_counter;  // tensor-core row kernel: work queue of the launch (zeroed by the launcher)
   unsigned long long* dbg;  // optional per-phase cycle counters (FRX_TC_DEBUG), else null
   // Long rows (tensor-core path): a row with more than FRX_SPLIT_MIN entries is cut into pieces of
   // FRX_PIECE entries whose partial SYRK sums are produced by a first launch (piece_mode = 1, one
@@ -73,26 +74,30 @@ int row_solve_generic_grid(int num_rows, int num_sms);
 bool row_solve_tc_supported(const RowParams& p);
 void launch_row_solve_tc(const RowParams& p, cudaStream_t s, int num_sms, long long* launches);
 
-// Dual-form row path (frx_row_wb.cu) for rows with at most FRX_WB_MAX entries: needs the eigenbasis of the
-// Gramian (frx_eig.cu) and the fixed-side factors rotated into it (frx_gemm.cu).
+// Dual-form row path (frx_row_wb.cu) for rows with at most FRX_WB_MAX entries: needs the tridiagonal form
+// G = H T H^T of the Gramian (frx_eig.cu) and the fixed-side factors rotated into that basis (frx_gemm.cu).
 constexpr int FRX_WB_MAX = 128;
 struct WbParams {
   const int* grp_slots;  // [num_groups][4]: (index into wb_rows << 2) | 32-entry chunk of that row, or -1
   const int* wb_rows;    // row ids solved by this path
   int num_groups;
-  const float* Et;       // [num_other x d] = E * Q
-  const float* lam;      // [d] eigenvalues of G
-  float* Xt;             // [num wb rows x d] rotated solutions (the caller applies Q^T)
+  const float* Et;       // [num_other x d] = E * H
+  const float* tdiag;    // [d] diagonal of T
+  const float* tsub;     // [d] tsub[j] = T[j][j-1], tsub[0] = 0
+  float* lsub;           // [num wb rows x d] scratch: bidiagonal factor of alpha*T + beta*I per row
+  float* rsd;            // [num wb rows x d] scratch: its Dl^(-1/2)
+  float* Xt;             // [num wb rows x d] rotated solutions (the caller applies H^T)
   int* counter;          // work queue (zeroed by the launcher)
 };
 bool row_solve_wb_supported(const RowParams& p);
-void launch_row_solve_wb(const RowParams& p, const WbParams& q, cudaStream_t s, int num_sms, long long* launches);
+void launch_row_solve_wb(const RowParams& p, const WbParams& q, int num_wb_rows, cudaStream_t s, int num_sms,
+                         long long* launches);
 
-// G = Q diag(lam) Q^T for the symmetric d x d Gramian (d = 128 / 256): Q row-major (column i = eigenvector i),
-// QT = Q^T, all fp32; info[0] = sweeps (negative: not converged).  Returns 0 on success.
-bool sym_eig_supported(int d);
-int launch_sym_eig(const float* G, int d, float* Q, float* QT, float* lam, int* info, cudaStream_t s,
-                   long long* launches);
+// G = H T H^T for the symmetric d x d Gramian (d = 128 / 256), T tridiagonal: tdiag[d], tsub[d] (tsub[j] =
+// T[j][j-1], tsub[0] = 0), H and HT = H^T row-major, all fp32.  Returns 0 on success.
+bool sym_tridiag_supported(int d);
+int launch_sym_tridiag(const float* G, int d, float* H, float* HT, float* tdiag, float* tsub, cudaStream_t s,
+                       long long* launches);
 
 // C[out(i)][:] = A[i][:] * B, A [M x d], B [d x d] row-major, out(i) = c_map[c_rows[i]] (either may be null).
 void launch_rows_gemm(const float* A, int M, int d, const float* B, float* C, const int* c_rows, const int* c_map,

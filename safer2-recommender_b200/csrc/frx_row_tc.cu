@@ -239,7 +239,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
   long long tstamp = clock64();
 #define FRX_DBG_LAP(slot) do { if (p.dbg && warp == P - 1 && lane == 0) { const long long now_ = clock64(); dbg_acc[slot] += (unsigned long long)(now_ - tstamp); tstamp = now_; } } while (0)
 
-  for (int ri = blockIdx.x; ri < num_work; ri += gridDim.x, ++row_count) {
+  // Work items come from a global queue: the first one is blockIdx.x, every later one is taken with an atomic
+  // add while the current item is being gathered (items are sorted longest first, so the queue balances the SMs
+  // and a CTA that starts late -- its SM was busy with another kernel -- simply takes fewer items).
+  __shared__ int next_item_s;
+  for (int ri = blockIdx.x; ri < num_work; ++row_count) {
+    if (tid == 0) next_item_s = (int)gridDim.x + atomicAdd(p.work_counter, 1);  // read after the next __syncthreads
     // A work item is a row, or (piece mode) one FRX_PIECE-entry piece of a long row.
     const int r = PIECE ? p.piece_row[ri] : p.order[ri];
     const int beg = p.ptr[r];
@@ -368,6 +373,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
       }
     }
     __syncthreads();
+    const int ri_next = next_item_s;  // stable until thread 0 writes it again at the top of the next item
     FRX_DBG_LAP(0);  // phase A (gather + SYRK)
 
     const RowScalars rs_row = row_scalars(p, r, n);
@@ -411,6 +417,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
       tc_fence_before();
       __syncthreads();
       tc_fence_after();
+      ri = ri_next;
       continue;
     }
     tc_fence_before();
@@ -645,7 +652,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
     float* xS = wsum;  // x_i of the solved panels, [D]
     if (!is_row_warp) {
       // meanwhile the other warps write alpha*G + beta*I of this CTA's NEXT row into the idle TMEM
-      const int rin = ri + (int)gridDim.x;
+      const int rin = ri_next;
       if (rin < p.num_rows) {
         const int rn = p.order[rin];
         const int nn = p.ptr[rn + 1] - p.ptr[rn];
@@ -700,6 +707,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
     tc_fence_before();
     __syncthreads();  // the aliased shared memory and TMEM are free for the next row
     FRX_DBG_LAP(5);  // back substitution + store
+    ri = ri_next;
   }
 
   if (p.dbg && warp == P - 1 && lane == 0) {
@@ -723,6 +731,7 @@ bool row_solve_tc_supported(const RowParams& p) {
 
 template <int D, int MODE>
 static void launch_tc_instance(const RowParams& p, int work, cudaStream_t s, int num_sms) {
+  cudaMemsetAsync(p.work_counter, 0, sizeof(int), s);
   const int smem = TcLayout<D>::kTotal + 1024;
   cudaFuncSetAttribute(row_solve_tc_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int grid = num_sms < work ? num_sms : work;

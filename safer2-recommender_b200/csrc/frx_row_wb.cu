@@ -1,30 +1,32 @@
 // Dual-form ("Woodbury") row kernel on tcgen05 / TMEM for rows with n <= 128 history entries, D = 128 / 256.
 //
 // The reference solves, per row,  (alpha*G + beta*I + sum_i s_i e_i e_i^T) x = sum_i q_i e_i  with a d x d
-// Cholesky (ials.h:88-144, safer2.h:104-163, safer2.h:166-221).  With G = Q diag(lam) Q^T (frx_eig.cu), the
-// rotated factors Et = E*Q and Dg = diag(1 / (alpha*lam + beta)) the push-through identity gives the SAME x as
-//     x = Q * Dg * Ft^T * y,     (I + Fh Fh^T) y = t,
-//     Ft = diag(sqrt(s)) Et[hist],   Fh = Ft * Dg^(1/2),   t_i = q_i / sqrt(s_i)
+// Cholesky (ials.h:88-144, safer2.h:104-163, safer2.h:166-221).  With G = H T H^T (Householder tridiagonal
+// form, frx_eig.cu), the rotated factors Et = E*H and T_r = alpha*T + beta*I = L Dl L^T (bidiagonal L: O(d) per
+// row, wb_row_factor_kernel) the push-through identity gives the SAME x as
+//     x = H * T_r^-1 * Ft^T * y,     (I + Fh Fh^T) y = t,
+//     Ft = diag(sqrt(s)) Et[hist],   Fh = Ft * L^-T * Dl^(-1/2),   t_i = q_i / sqrt(s_i)
 // i.e. an n x n SPD system instead of a d x d one: n^2 d SYRK flops instead of n d^2, n^3/3 Cholesky flops
 // instead of d^3/3, and 128 TMEM columns per system instead of 384, so that several systems are in flight
 // per SM and the latency-bound factorisation of one hides under the tensor-core work of the others.
 //
 // Work unit = a GROUP of up to four 32-entry slots (128 entries): one row of 97..128 entries, or several
 // shorter rows packed side by side (their cross blocks in the 128 x 128 product are never read).
-// Roles inside the persistent CTA (one per SM, 20 warps):
+// Roles inside the persistent CTA (one per SM, 18 warps):
 //   scheduler warp  takes group ids from a global atomic counter and publishes the group's slot descriptors
-//                   and per-row scalars in a small shared-memory ring;
-//   6 loader warps  unit = (slot, 32-feature chunk): lane = history entry, 128 contiguous bytes of the rotated
-//                   factor row, scaled by sqrt(s_i) * rsqrt(alpha*lam_j + beta), split into tf32 hi + lo and
-//                   stored as K-major SWIZZLE_128B operand tiles [128 entries][32 features] (no transpose:
-//                   the contraction runs over the feature dimension here);
+//                   in a small shared-memory ring;
+//   4 loader warps  warp s = slot s of every group, its 32-feature chunks in order: lane = history entry,
+//                   128 contiguous bytes of the rotated factor row per chunk (next chunk prefetched), the
+//                   bidiagonal forward recurrence w_j = sqrt(s) e_j - l_j w_(j-1) along the features, scaled by
+//                   Dl^(-1/2), split into tf32 hi + lo and stored as K-major SWIZZLE_128B operand tiles
+//                   [128 entries][32 features] (no transpose: the contraction runs over the features here);
 //   MMA warp        C += Fh_chunk Fh_chunk^T as hi*hi + hi*lo + lo*hi (3xTF32), M = N = 128, into one of three
 //                   128-column TMEM accumulators; 3 operand stages, mbarrier full/empty pipeline;
 //   3 solver sets   (4 warps each, warp w <-> slot w <-> TMEM lanes 32w..32w+31, thread = system row):
 //                   blocked right-looking Cholesky of the row's diagonal block(s) with 32-wide panels, forward
 //                   substitution fused, factor kept in TMEM, back substitution with inv(L11) per panel, then
-//                   xt = Dg * sum_i sqrt(s_i) y_i Et[c_i]  (second gather, lane = feature) written to the
-//                   rotated-solution scratch; a GEMM with Q^T (frx_gemm.cu) takes it back to the original basis.
+//                   g = sum_i sqrt(s_i) y_i Et[c_i]  (second gather, lane = feature) and xt = T_r^-1 g by the two
+//                   bidiagonal sweeps; a GEMM with H^T (frx_gemm.cu) takes xt back to the original basis.
 #include "frx_tc_common.cuh"
 
 namespace frx {
@@ -39,7 +41,7 @@ constexpr int WB_RING = 4;     // group descriptors in flight
 constexpr int WB_MMA_WARP = 4 * WB_NACC;
 constexpr int WB_SCHED_WARP = WB_MMA_WARP + 1;
 constexpr int WB_LOADER0 = WB_SCHED_WARP + 1;
-constexpr int WB_NLOADER = 6;
+constexpr int WB_NLOADER = 4;   // loader warp s serves slot s of every group
 constexpr int WB_THREADS = (WB_LOADER0 + WB_NLOADER) * 32;
 
 constexpr int WB_TILE_BYTES = 128 * 128;           // [128 entries][32 features] fp32
@@ -49,7 +51,7 @@ struct WbRing {  // one published group
   int gid;
   int desc[4];   // (wb row index << 2) | 32-entry chunk of the row, or -1
   int row[4], n[4], beg[4];
-  float alpha[4], beta[4], bscale[4];
+  float bscale[4];
 };
 
 struct WbSet {  // per solver set / accumulator slot
@@ -70,9 +72,8 @@ struct WbLayout {
   static constexpr int kStagesOff = 0;
   static constexpr int kSetOff = WB_NSTAGE * WB_STAGE_BYTES;
   static constexpr int kRingOff = kSetOff + WB_NACC * (int)sizeof(WbSet);
-  static constexpr int kLamOff = kRingOff + WB_RING * (int)sizeof(WbRing);
-  static constexpr int kSdOff = kLamOff + D * 4;
-  static constexpr int kBarOff = ((kSdOff + WB_NLOADER * 32 * 4 + 15) / 16) * 16;
+  static constexpr int kSdOff = ((kRingOff + WB_RING * (int)sizeof(WbRing) + 15) / 16) * 16;
+  static constexpr int kBarOff = ((kSdOff + WB_NLOADER * 64 * 4 + 15) / 16) * 16;
   static constexpr int kNumBars = 2 * WB_NSTAGE + 3 * WB_NACC + 2 * WB_RING;
   static constexpr int kTotal = kBarOff + kNumBars * 8;
 };
@@ -85,12 +86,10 @@ template <int D>
 __global__ void __launch_bounds__(WB_THREADS, 1) row_solve_wb_kernel(RowParams p, WbParams q) {
   using L = WbLayout<D>;
   constexpr int KC = L::KC;
-  constexpr int NU = 4 * KC;  // loader units per group
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   WbSet* sets = reinterpret_cast<WbSet*>(sm + L::kSetOff);
   WbRing* ring = reinterpret_cast<WbRing*>(sm + L::kRingOff);
-  float* lamS = reinterpret_cast<float*>(sm + L::kLamOff);
   float* sdS = reinterpret_cast<float*>(sm + L::kSdOff);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::kBarOff);
   uint64_t* full_bar = bars;                           // [NSTAGE] 4 unit arrivals
@@ -109,7 +108,6 @@ __global__ void __launch_bounds__(WB_THREADS, 1) row_solve_wb_kernel(RowParams p
     for (int i = 0; i < WB_RING; ++i) { mbar_init(&gq_full[i], 1); mbar_init(&gq_empty[i], WB_NLOADER + 1 + 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < D; i += WB_THREADS) lamS[i] = q.lam[i];
   if (warp == WB_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -119,6 +117,9 @@ __global__ void __launch_bounds__(WB_THREADS, 1) row_solve_wb_kernel(RowParams p
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   const uint32_t sm_addr = smem_u32(sm);
+  // optional cycle counters (FRX_TC_DEBUG): solver set 0 / warp 0 and the MMA warp
+  long long tstamp = clock64();
+#define WB_LAP(slot) do { if (p.dbg && lane == 0 && (warp == 0 || warp == WB_MMA_WARP)) { const long long now_ = clock64(); atomicAdd(p.dbg + (slot), (unsigned long long)(now_ - tstamp)); tstamp = now_; } } while (0)
 
   if (warp == WB_SCHED_WARP) {
     // ======================= scheduler =======================
@@ -142,10 +143,10 @@ __global__ void __launch_bounds__(WB_THREADS, 1) row_solve_wb_kernel(RowParams p
           const int beg = __ldg(p.ptr + r), n = __ldg(p.ptr + r + 1) - beg;
           const RowScalars s = row_scalars(p, r, n);
           e.row[lane] = r; e.n[lane] = n; e.beg[lane] = beg;
-          e.alpha[lane] = s.alpha; e.beta[lane] = s.beta; e.bscale[lane] = s.bscale;
+          e.bscale[lane] = s.bscale;
         } else {
           e.row[lane] = -1; e.n[lane] = 0; e.beg[lane] = 0;
-          e.alpha[lane] = 0.f; e.beta[lane] = 1.f; e.bscale[lane] = 0.f;
+          e.bscale[lane] = 0.f;
         }
       }
       __syncwarp();
@@ -154,8 +155,11 @@ __global__ void __launch_bounds__(WB_THREADS, 1) row_solve_wb_kernel(RowParams p
     }
   } else if (warp >= WB_LOADER0) {
     // ======================= loaders =======================
+    // Loader warp s fills slot s of every group, chunk by chunk in feature order (the bidiagonal recurrence runs
+    // along the features).  Every loader warp therefore passes through every use of every stage: the parity
+    // waits below are only valid for a waiter that is at most one phase behind the barrier.
     const int lw = warp - WB_LOADER0;
-    float* sd = sdS + lw * 32;
+    float* sd = sdS + lw * 64;  // [0,32) l_j, [32,64) Dl_j^(-1/2) of the current chunk
     for (uint32_t gseq = 0;; ++gseq) {
       const uint32_t rsi = gseq % WB_RING;
       mbar_wait(&gq_full[rsi], (gseq / WB_RING) & 1);
@@ -163,61 +167,84 @@ __global__ void __launch_bounds__(WB_THREADS, 1) row_solve_wb_kernel(RowParams p
       if (e.gid < 0) break;
       const uint32_t slot = gseq % WB_NACC, ause = gseq / WB_NACC;
       WbSet& S = sets[slot];
-      uint32_t uu = (uint32_t)((lw + WB_NLOADER - (int)((gseq * NU) % WB_NLOADER)) % WB_NLOADER);
-      for (; uu < (uint32_t)NU; uu += WB_NLOADER) {
-        const int k = (int)(uu >> 2), s = (int)(uu & 3);
-        const uint32_t cs = gseq * KC + (uint32_t)k, st = cs % WB_NSTAGE, use = cs / WB_NSTAGE;
-        if (use > 0) mbar_wait(&empty_bar[st], (use - 1) & 1);
+      {
+        const int s = lw;
         const int desc = e.desc[s];
-        if (desc >= 0) {
-          if (k == 0 && ause > 0) mbar_wait(&acc_empty[slot], (ause - 1) & 1);  // per-slot arrays are free again
-          const int n = e.n[s], beg = e.beg[s];
-          const int en = 32 * (desc & 3) + lane;  // entry index within the row
-          const bool valid = en < n;
-          const float alpha = e.alpha[s], beta = e.beta[s];
-          sd[lane] = rsqrtf(fmaf(alpha, lamS[32 * k + lane], beta));
-          float4 v[8];
-          int c = 0;
-          float sw = 0.f, qw = 0.f;
-          if (valid) {
-            c = __ldg(p.col + beg + en);
-            const float4* src = reinterpret_cast<const float4*>(q.Et + (size_t)c * D + 32 * k);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __ldg(src + j);
-            sw = 1.f; qw = 1.f;
-            if (p.mode == RM_SAFER_V) { const float w = __ldg(p.entry_w + c); sw = w; qw = w; }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          const float sq = sqrtf(sw);
-          __syncwarp();
-          uint8_t* hi_tile = sm + st * WB_STAGE_BYTES;
-          uint8_t* lo_tile = hi_tile + WB_TILE_BYTES;
-          const int mn = 32 * s + lane;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 s4 = reinterpret_cast<const float4*>(sd)[j];
-            const float x4[4] = {v[j].x * (sq * s4.x), v[j].y * (sq * s4.y), v[j].z * (sq * s4.z), v[j].w * (sq * s4.w)};
-            float hi[4], lo[4];
-#pragma unroll
-            for (int t4 = 0; t4 < 4; ++t4) {
-              hi[t4] = __uint_as_float(__float_as_uint(x4[t4]) & 0xffffe000u);
-              lo[t4] = x4[t4] - hi[t4];
-            }
-            const uint32_t off = tile_chunk_off(mn, j);
-            *reinterpret_cast<float4*>(hi_tile + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<float4*>(lo_tile + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-          }
-          if (k == 0) {
-            S.cidx[mn] = c;
-            S.sqs[mn] = sq;
-            S.tvec[mn] = (valid && sw > 0.f) ? e.bscale[s] * qw / sq : 0.f;
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const int n = e.n[s], beg = e.beg[s];
+        const int en = 32 * (desc & 3) + lane;  // entry index within the row
+        const bool valid = desc >= 0 && en < n;
+        const int mn = 32 * s + lane;
+        int c = 0;
+        float sw = 0.f, qw = 0.f;
+        if (valid) {
+          c = __ldg(p.col + beg + en);
+          sw = 1.f; qw = 1.f;
+          if (p.mode == RM_SAFER_V) { const float w = __ldg(p.entry_w + c); sw = w; qw = w; }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_bar[st]);
+        const float sq = sqrtf(sw);
+        const float4* src = reinterpret_cast<const float4*>(q.Et + (size_t)c * D);
+        const float* lrow = q.lsub + (size_t)(desc >= 0 ? (desc >> 2) : 0) * D;
+        const float* rrow = q.rsd + (size_t)(desc >= 0 ? (desc >> 2) : 0) * D;
+        float4 v[8];
+        float lnext = 0.f, rnext = 0.f;
+        if (desc >= 0) {
+          lnext = __ldg(lrow + lane);
+          rnext = __ldg(rrow + lane);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = valid ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float wprev = 0.f;  // w_(j-1) of the recurrence, carried across chunks
+        for (int k = 0; k < KC; ++k) {
+          const uint32_t cs = gseq * KC + (uint32_t)k, st = cs % WB_NSTAGE, use = cs / WB_NSTAGE;
+          if (use > 0) mbar_wait(&empty_bar[st], (use - 1) & 1);
+          if (desc >= 0) {
+            if (k == 0 && ause > 0) mbar_wait(&acc_empty[slot], (ause - 1) & 1);  // per-slot arrays are free again
+            __syncwarp();
+            sd[lane] = lnext;
+            sd[32 + lane] = rnext;
+            float4 vc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) vc[j] = v[j];
+            if (k + 1 < KC) {  // next chunk in flight while this one is processed
+              lnext = __ldg(lrow + 32 * (k + 1) + lane);
+              rnext = __ldg(rrow + 32 * (k + 1) + lane);
+              if (valid) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __ldg(src + 8 * (k + 1) + j);
+              }
+            }
+            __syncwarp();
+            uint8_t* hi_tile = sm + st * WB_STAGE_BYTES;
+            uint8_t* lo_tile = hi_tile + WB_TILE_BYTES;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 l4 = reinterpret_cast<const float4*>(sd)[j];
+              const float4 r4 = reinterpret_cast<const float4*>(sd + 32)[j];
+              float x4[4];
+              wprev = fmaf(-l4.x, wprev, sq * vc[j].x); x4[0] = wprev * r4.x;
+              wprev = fmaf(-l4.y, wprev, sq * vc[j].y); x4[1] = wprev * r4.y;
+              wprev = fmaf(-l4.z, wprev, sq * vc[j].z); x4[2] = wprev * r4.z;
+              wprev = fmaf(-l4.w, wprev, sq * vc[j].w); x4[3] = wprev * r4.w;
+              float hi[4], lo[4];
+#pragma unroll
+              for (int t4 = 0; t4 < 4; ++t4) {
+                hi[t4] = __uint_as_float(__float_as_uint(x4[t4]) & 0xffffe000u);
+                lo[t4] = x4[t4] - hi[t4];
+              }
+              const uint32_t off = tile_chunk_off(mn, j);
+              *reinterpret_cast<float4*>(hi_tile + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<float4*>(lo_tile + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            if (k == 0) {
+              S.cidx[mn] = c;
+              S.sqs[mn] = sq;
+              S.tvec[mn] = (valid && sw > 0.f) ? e.bscale[s] * qw / sq : 0.f;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full_bar[st]);
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&gq_empty[rsi]);
@@ -233,13 +260,16 @@ __global__ void __launch_bounds__(WB_THREADS, 1) row_solve_wb_kernel(RowParams p
       if (lane == 0) mbar_arrive(&gq_empty[rsi]);
       if (gid < 0) break;
       const uint32_t slot = gseq % WB_NACC, ause = gseq / WB_NACC;
+      WB_LAP(7);
       if (ause > 0) mbar_wait(&acc_empty[slot], (ause - 1) & 1);
       tc_fence_after();
+      WB_LAP(4);
       const uint32_t d_tmem = tmem_base + 128u * slot;
       for (int k = 0; k < KC; ++k) {
         const uint32_t cs = gseq * KC + (uint32_t)k, st = cs % WB_NSTAGE, use = cs / WB_NSTAGE;
         mbar_wait(&full_bar[st], use & 1);
         tc_fence_after();
+        WB_LAP(5);
         // chunk 0 carries the per-slot arrays: hand the loaders' writes on to the solver set (acquire above,
         // release here: the ordering is transitive)
         if (k == 0 && lane == 0) mbar_arrive(&acc_meta[slot]);
@@ -256,6 +286,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) row_solve_wb_kernel(RowParams p
           if (k == KC - 1) umma_commit(&acc_full[slot]);
         }
         __syncwarp();
+        WB_LAP(6);
       }
     }
   } else {
@@ -284,6 +315,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) row_solve_wb_kernel(RowParams p
       mbar_wait(&acc_meta[set], ause & 1);
       mbar_wait(&acc_full[set], ause & 1);
       tc_fence_after();
+      WB_LAP(0);
       float b_reg = used ? S.tvec[32 * w + lane] : 0.f;  // t_i, then y1_i, then y_i
       float a[32];
 
@@ -437,6 +469,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) row_solve_wb_kernel(RowParams p
         set_barrier(set);  // B: buffers may be overwritten by the next step
       }
 
+      WB_LAP(1);
       // ---- back substitution L^T y = y1, panel by panel from the bottom ----
       for (int k = nsteps - 1; k >= 0; --k) {
         if (used && rel == k) {
@@ -469,15 +502,20 @@ __global__ void __launch_bounds__(WB_THREADS, 1) row_solve_wb_kernel(RowParams p
       S.coef[32 * w + lane] = used ? S.sqs[32 * w + lane] * b_reg : 0.f;
       tc_fence_before();
       set_barrier(set);
+      WB_LAP(2);
 
-      // ---- xt = Dg * sum_i coef_i Et[c_i]  (lane = feature; warp w takes features [w*D/4, (w+1)*D/4)) ----
+      // ---- g = sum_i coef_i Et[c_i]  (lane = feature; warp w takes features [w*D/4, (w+1)*D/4)) ----
+      // S.buf is free now: [0] g, [1] l, [2] Dl^(-1/2), [3] xt, each [4 row slots][D]
       constexpr int FW = D / 4, F = FW / 32;
+      float* gS = S.buf[0];
+      float* lS = S.buf[1];
+      float* rS = S.buf[2];
+      float* xS = S.buf[3];
 #pragma unroll 1
       for (int s = 0; s < 4; ++s) {
         int desc = -1, n = 0;
-        float alpha = 0.f, beta = 1.f;
 #pragma unroll
-        for (int s2 = 0; s2 < 4; ++s2) if (s2 == s) { desc = e.desc[s2]; n = e.n[s2]; alpha = e.alpha[s2]; beta = e.beta[s2]; }
+        for (int s2 = 0; s2 < 4; ++s2) if (s2 == s) { desc = e.desc[s2]; n = e.n[s2]; }
         if (desc < 0 || (desc & 3) != 0) continue;  // rows start at their chunk 0
         const int f0 = w * FW + lane * F;
         float acc[F];
@@ -486,17 +524,17 @@ __global__ void __launch_bounds__(WB_THREADS, 1) row_solve_wb_kernel(RowParams p
         const int* ci = S.cidx + 32 * s;
         const float* cf = S.coef + 32 * s;
         int en = 0;
-        for (; en + 4 <= n; en += 4) {
-          float vv[4][F];
+        for (; en + 8 <= n; en += 8) {
+          float vv[8][F];
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
+          for (int t = 0; t < 8; ++t) {
             const float* src = q.Et + (size_t)ci[en + t] * D + f0;
             if (F == 2) { const float2 x2 = __ldg(reinterpret_cast<const float2*>(src)); vv[t][0] = x2.x; vv[t][F - 1] = x2.y; }
             else if (F == 4) { const float4 x4 = __ldg(reinterpret_cast<const float4*>(src)); vv[t][0] = x4.x; vv[t][1 % F] = x4.y; vv[t][2 % F] = x4.z; vv[t][3 % F] = x4.w; }
             else vv[t][0] = __ldg(src);
           }
 #pragma unroll
-          for (int t = 0; t < 4; ++t)
+          for (int t = 0; t < 8; ++t)
 #pragma unroll
             for (int f = 0; f < F; ++f) acc[f] = fmaf(cf[en + t], vv[t][f], acc[f]);
         }
@@ -505,11 +543,64 @@ __global__ void __launch_bounds__(WB_THREADS, 1) row_solve_wb_kernel(RowParams p
 #pragma unroll
           for (int f = 0; f < F; ++f) acc[f] = fmaf(cf[en], __ldg(src + f), acc[f]);
         }
-        float* dst = q.Xt + (size_t)(desc >> 2) * D + f0;
+        const size_t rowoff = (size_t)(desc >> 2) * D;
 #pragma unroll
-        for (int f = 0; f < F; ++f) dst[f] = acc[f] / fmaf(alpha, lamS[f0 + f], beta);
+        for (int f = 0; f < F; ++f) {
+          gS[s * D + f0 + f] = acc[f];
+          lS[s * D + f0 + f] = __ldg(q.lsub + rowoff + f0 + f);
+          rS[s * D + f0 + f] = __ldg(q.rsd + rowoff + f0 + f);
+        }
+      }
+      set_barrier(set);
+      // ---- xt = L^-T Dl^-1 L^-1 g: two bidiagonal sweeps, one lane per row ----
+      if (w == 0 && lane < 4) {
+        int desc = -1;
+#pragma unroll
+        for (int s2 = 0; s2 < 4; ++s2) if (s2 == lane) desc = e.desc[s2];
+        if (desc >= 0 && (desc & 3) == 0) {
+          const float* g = gS + lane * D;
+          const float* l = lS + lane * D;
+          const float* r = rS + lane * D;
+          float* x = xS + lane * D;
+          float u = 0.f;
+#pragma unroll 4
+          for (int j4 = 0; j4 < D / 4; ++j4) {
+            const float4 g4 = reinterpret_cast<const float4*>(g)[j4];
+            const float4 l4 = reinterpret_cast<const float4*>(l)[j4];
+            const float4 r4 = reinterpret_cast<const float4*>(r)[j4];
+            float4 o;
+            u = fmaf(-l4.x, u, g4.x); o.x = u * (r4.x * r4.x);
+            u = fmaf(-l4.y, u, g4.y); o.y = u * (r4.y * r4.y);
+            u = fmaf(-l4.z, u, g4.z); o.z = u * (r4.z * r4.z);
+            u = fmaf(-l4.w, u, g4.w); o.w = u * (r4.w * r4.w);
+            reinterpret_cast<float4*>(x)[j4] = o;
+          }
+          float xn = 0.f, ln = 0.f;  // x_(j+1), l_(j+1)
+#pragma unroll 4
+          for (int j4 = D / 4 - 1; j4 >= 0; --j4) {
+            float4 o = reinterpret_cast<const float4*>(x)[j4];
+            const float4 l4 = reinterpret_cast<const float4*>(l)[j4];
+            o.w = fmaf(-ln, xn, o.w);
+            o.z = fmaf(-l4.w, o.w, o.z);
+            o.y = fmaf(-l4.z, o.z, o.y);
+            o.x = fmaf(-l4.y, o.y, o.x);
+            xn = o.x; ln = l4.x;
+            reinterpret_cast<float4*>(x)[j4] = o;
+          }
+        }
+      }
+      set_barrier(set);
+#pragma unroll 1
+      for (int s = 0; s < 4; ++s) {
+        int desc = -1;
+#pragma unroll
+        for (int s2 = 0; s2 < 4; ++s2) if (s2 == s) desc = e.desc[s2];
+        if (desc < 0 || (desc & 3) != 0) continue;
+        float* dst = q.Xt + (size_t)(desc >> 2) * D;
+        for (int f = w * 32 + lane; f < D; f += 128) dst[f] = xS[s * D + f];
       }
       __syncwarp();
+      WB_LAP(3);
       if (lane == 0) mbar_arrive(&acc_empty[set]);  // TMEM slot and the per-slot arrays are free
     }
   }
@@ -520,8 +611,51 @@ __global__ void __launch_bounds__(WB_THREADS, 1) row_solve_wb_kernel(RowParams p
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
+// Per-row factors of T_r = alpha*T + beta*I = L Dl L^T (L unit lower bidiagonal): lsub[j] = L[j][j-1]
+// (lsub[0] = 0) and rsd[j] = Dl_j^(-1/2), for every row of the dual-form path.  Lane = row (the recurrence is
+// sequential in j); 32 x 32 tiles go through shared memory so that the rows are written coalesced.
 template <int D>
-void launch_wb_instance(const RowParams& p, const WbParams& q, cudaStream_t s, int num_sms) {
+__global__ void __launch_bounds__(128) wb_row_factor_kernel(RowParams p, WbParams q, int nwb) {
+  __shared__ float tdS[D], tsS[D];
+  __shared__ float tile[4][2][32][33];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < D; i += 128) { tdS[i] = q.tdiag[i]; tsS[i] = q.tsub[i]; }
+  __syncthreads();
+  const int i0 = (blockIdx.x * 4 + warp) * 32;
+  if (i0 >= nwb) return;
+  const int i = i0 + lane;
+  float alpha = 0.f, beta = 1.f;
+  if (i < nwb) {
+    const int r = __ldg(q.wb_rows + i);
+    const RowScalars s = row_scalars(p, r, __ldg(p.ptr + r + 1) - __ldg(p.ptr + r));
+    alpha = s.alpha; beta = s.beta;
+  }
+  float delta = 1.f;
+  bool bad = false;
+  for (int c = 0; c < D / 32; ++c) {
+#pragma unroll 8
+    for (int jj = 0; jj < 32; ++jj) {
+      const int j = 32 * c + jj;
+      const float ab = alpha * tsS[j];          // tsub[0] = 0
+      const float l = j ? ab / delta : 0.f;
+      delta = fmaf(alpha, tdS[j], beta) - ab * l;
+      bad |= !(delta > 0.f);
+      tile[warp][0][lane][jj] = l;
+      tile[warp][1][lane][jj] = rsqrtf(delta);
+    }
+    __syncwarp();
+    for (int rr = 0; rr < 32 && i0 + rr < nwb; ++rr) {
+      q.lsub[(size_t)(i0 + rr) * D + 32 * c + lane] = tile[warp][0][rr][lane];
+      q.rsd[(size_t)(i0 + rr) * D + 32 * c + lane] = tile[warp][1][rr][lane];
+    }
+    __syncwarp();
+  }
+  if (bad && i < nwb) atomicExch(p.status, 1);  // alpha*G + beta*I is not positive definite
+}
+
+template <int D>
+void launch_wb_instance(const RowParams& p, const WbParams& q, int nwb, cudaStream_t s, int num_sms) {
+  wb_row_factor_kernel<D><<<(nwb + 127) / 128, 128, 0, s>>>(p, q, nwb);
   const int smem = WbLayout<D>::kTotal + 1024;
   cudaFuncSetAttribute(row_solve_wb_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int grid = num_sms < q.num_groups ? num_sms : q.num_groups;
@@ -535,12 +669,13 @@ bool row_solve_wb_supported(const RowParams& p) {
   return mode_ok && p.cs == 0 && p.bd == p.d && (p.d == 128 || p.d == 256);
 }
 
-void launch_row_solve_wb(const RowParams& p, const WbParams& q, cudaStream_t s, int num_sms, long long* launches) {
-  if (q.num_groups <= 0) return;
+void launch_row_solve_wb(const RowParams& p, const WbParams& q, int nwb, cudaStream_t s, int num_sms,
+                         long long* launches) {
+  if (q.num_groups <= 0 || nwb <= 0) return;
   cudaMemsetAsync(q.counter, 0, sizeof(int), s);
-  if (p.d == 256) launch_wb_instance<256>(p, q, s, num_sms);
-  else launch_wb_instance<128>(p, q, s, num_sms);
-  if (launches) ++*launches;
+  if (p.d == 256) launch_wb_instance<256>(p, q, nwb, s, num_sms);
+  else launch_wb_instance<128>(p, q, nwb, s, num_sms);
+  if (launches) *launches += 2;
 }
 
 }  // namespace frx

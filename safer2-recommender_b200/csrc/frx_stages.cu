@@ -440,52 +440,70 @@ __global__ void user_weights_kernel(const float* __restrict__ loss, const float*
 // double -> grid barrier -> every CTA adds the partials in the same fixed order,
 // so all CTAs take identical branches.
 // ---------------------------------------------------------------------------
+constexpr int XI_MAXK = 8;  // Armijo trial points evaluated per pass
 struct QEval { float value, grad, H; };
 
-__device__ QEval evaluate_quantile(const XiParams& p, const int* idx, int n, float xi, int parity,
-                                   double* sh, cg::grid_group& grid) {
-  double s_cdf = 0.0, s_pdf = 0.0, s_loss = 0.0;
+// K evaluation points at once: one pass over the (sub-sampled) losses, one grid barrier.  For every point the
+// per-thread / per-CTA / cross-CTA summation order is the one a single evaluation uses, so the values (and with
+// them the Newton / Armijo branches) do not depend on K.
+template <int K>
+__device__ void evaluate_quantile(const XiParams& p, const int* idx, int n, const float (&xi)[K], int parity,
+                                  double* sh, cg::grid_group& grid, QEval (&out)[K]) {
+  double s_cdf[K], s_pdf[K], s_loss[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) s_cdf[k] = s_pdf[k] = s_loss[k] = 0.0;
   const float h = p.bandwidth, alpha = p.alpha;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float l = idx ? p.loss[idx[i]] : p.loss[i];
-    const float u = l - xi;
-    if (p.epanechnikov) {
-      s_cdf += epanechnikov_kernel_cdf(-u, h);
-      s_pdf += epanechnikov_kernel(-u, h);
-      s_loss += epanechnikov_loss(u, h, alpha);
-    } else {
-      s_cdf += gaussian_kernel_cdf(-u, h);
-      s_pdf += gaussian_kernel(-u, h);
-      s_loss += gaussian_loss(u, h, alpha);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float u = l - xi[k];
+      if (p.epanechnikov) {
+        s_cdf[k] += epanechnikov_kernel_cdf(-u, h);
+        s_pdf[k] += epanechnikov_kernel(-u, h);
+        s_loss[k] += epanechnikov_loss(u, h, alpha);
+      } else {
+        s_cdf[k] += gaussian_kernel_cdf(-u, h);
+        s_pdf[k] += gaussian_kernel(-u, h);
+        s_loss[k] += gaussian_loss(u, h, alpha);
+      }
     }
   }
-  s_cdf = block_sum_d(s_cdf, sh);
-  s_pdf = block_sum_d(s_pdf, sh);
-  s_loss = block_sum_d(s_loss, sh);
-  double* part = p.partials + (size_t)parity * gridDim.x * 3;
-  if (threadIdx.x == 0) {
-    part[blockIdx.x * 3 + 0] = s_cdf;
-    part[blockIdx.x * 3 + 1] = s_pdf;
-    part[blockIdx.x * 3 + 2] = s_loss;
+  double* part = p.partials + (size_t)parity * gridDim.x * (3 * XI_MAXK);
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const double a = block_sum_d(s_cdf[k], sh);
+    const double b = block_sum_d(s_pdf[k], sh);
+    const double c = block_sum_d(s_loss[k], sh);
+    if (threadIdx.x == 0) {
+      part[(size_t)blockIdx.x * (3 * XI_MAXK) + 3 * k + 0] = a;
+      part[(size_t)blockIdx.x * (3 * XI_MAXK) + 3 * k + 1] = b;
+      part[(size_t)blockIdx.x * (3 * XI_MAXK) + 3 * k + 2] = c;
+    }
   }
   grid.sync();
-  double t_cdf = 0.0, t_pdf = 0.0, t_loss = 0.0;
-  for (int b = 0; b < (int)gridDim.x; ++b) {
-    t_cdf += part[b * 3 + 0];
-    t_pdf += part[b * 3 + 1];
-    t_loss += part[b * 3 + 2];
+  // thread q < 3K adds quantity q over the CTAs in CTA order (the fixed order every CTA repeats)
+  double* tot = sh + 40;
+  if (threadIdx.x < 3 * K) {
+    double t = 0.0;
+    for (int b = 0; b < (int)gridDim.x; ++b) t += part[(size_t)b * (3 * XI_MAXK) + threadIdx.x];
+    tot[threadIdx.x] = t;
   }
-  const float mean_cdf = (float)(t_cdf / n), mean_pdf = (float)(t_pdf / n), mean_loss = (float)(t_loss / n);
-  QEval q;
-  q.grad = (-(1 - alpha) + mean_cdf) / alpha;  // safer2.h:659-686
-  q.H = mean_pdf / alpha;
-  q.value = mean_loss / alpha;
-  return q;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float mean_cdf = (float)(tot[3 * k] / n), mean_pdf = (float)(tot[3 * k + 1] / n),
+                mean_loss = (float)(tot[3 * k + 2] / n);
+    out[k].grad = (-(1 - alpha) + mean_cdf) / alpha;  // safer2.h:659-686
+    out[k].H = mean_pdf / alpha;
+    out[k].value = mean_loss / alpha;
+  }
+  __syncthreads();  // tot is reused by the next evaluation
 }
 
 __global__ void __launch_bounds__(256) xi_newton_kernel(XiParams p) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ double sh[33];
+  __shared__ double sh[40 + 3 * XI_MAXK];
   int parity = 0;
   float xi;
   if (p.start_from_mean) {  // Initialize: prev_xi = user_loss_.mean() (safer2.h:822)
@@ -493,11 +511,11 @@ __global__ void __launch_bounds__(256) xi_newton_kernel(XiParams p) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.num_users; i += gridDim.x * blockDim.x)
       s += (double)p.loss[i];
     s = block_sum_d(s, sh);
-    double* part = p.partials + (size_t)parity * gridDim.x * 3;
-    if (threadIdx.x == 0) part[blockIdx.x * 3] = s;
+    double* part = p.partials + (size_t)parity * gridDim.x * (3 * XI_MAXK);
+    if (threadIdx.x == 0) part[(size_t)blockIdx.x * (3 * XI_MAXK)] = s;
     grid.sync();
     double t = 0.0;
-    for (int b = 0; b < (int)gridDim.x; ++b) t += part[b * 3];
+    for (int b = 0; b < (int)gridDim.x; ++b) t += part[(size_t)b * (3 * XI_MAXK)];
     xi = (float)(t / p.num_users);
     parity ^= 1;
   } else {
@@ -506,21 +524,41 @@ __global__ void __launch_bounds__(256) xi_newton_kernel(XiParams p) {
   for (int t = 0; t < p.iters; ++t) {
     const int* idx = p.snr_idx ? p.snr_idx + (size_t)t * p.n_samples : nullptr;
     const int n = p.snr_idx ? p.n_samples : p.num_users;
-    // ComputeXiDirection, safer2.h:692-712
-    const QEval e0 = evaluate_quantile(p, idx, n, xi, parity, sh, grid);
-    parity ^= 1;
-    const float d = e0.grad / e0.H;
+    // ComputeXiDirection, safer2.h:692-712.  The reference halves gamma until the Armijo test passes (at most 32
+    // times), one EvaluateQuantile per trial; here the trial points are evaluated XI_MAXK at a time and the first
+    // one that passes is taken: same values, same choice, two grid barriers per Newton step in the usual case.
+    QEval e0[1];
+    {
+      const float x0[1] = {xi};
+      evaluate_quantile<1>(p, idx, n, x0, parity, sh, grid, e0);
+      parity ^= 1;
+    }
+    const float d = e0[0].grad / e0[0].H;
     const float c = 1e-4f;
     float gamma = 1.0f;
-    float x = xi + gamma * (-d);
-    for (int k = 0; k < 32; k++) {
-      const QEval ex = evaluate_quantile(p, idx, n, x, parity, sh, grid);
+    bool accepted = false;
+    for (int kb = 0; kb < 32 && !accepted; kb += XI_MAXK) {
+      float xs[XI_MAXK], gs[XI_MAXK];
+      float g = gamma;
+#pragma unroll
+      for (int j = 0; j < XI_MAXK; ++j) {
+        gs[j] = g;
+        xs[j] = xi + g * (-d);
+        g *= 0.5f;
+      }
+      QEval ex[XI_MAXK];
+      evaluate_quantile<XI_MAXK>(p, idx, n, xs, parity, sh, grid, ex);
       parity ^= 1;
-      if (ex.value > e0.value + c * gamma * ex.grad * (-d)) {  // B-6: trial point's gradient
-        gamma *= 0.5f;
-        x = xi + gamma * (-d);
-      } else {
-        break;
+#pragma unroll
+      for (int j = 0; j < XI_MAXK; ++j) {
+        if (!accepted) {
+          if (ex[j].value > e0[0].value + c * gs[j] * ex[j].grad * (-d)) {  // B-6: trial point's gradient
+            gamma = gs[j] * 0.5f;
+          } else {
+            gamma = gs[j];
+            accepted = true;
+          }
+        }
       }
     }
     xi = xi + (-gamma * d);
@@ -707,7 +745,7 @@ void launch_user_weights(const float* loss, const float* hist_size, int num_user
   if (launches) ++*launches;
 }
 
-size_t xi_partials_doubles(int num_sms) { return (size_t)2 * num_sms * 3; }
+size_t xi_partials_doubles(int num_sms) { return (size_t)2 * num_sms * 3 * XI_MAXK; }
 
 int launch_xi_newton(const XiParams& p_in, cudaStream_t s, int num_sms, long long* launches) {
   XiParams p = p_in;

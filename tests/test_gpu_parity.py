@@ -290,22 +290,22 @@ def test_tensor_core_row_kernel_epoch(pkg, O, ctx, name, cfg, d):
 
 
 @pytest.mark.parametrize("d", [128, 256])
-def test_sym_eig_of_a_gramian(ctx, d):
-    """The cluster Jacobi kernel behind the dual-form row path: G = Q diag(lam) Q^T to fp32 accuracy, Q
-    orthogonal, eigenvalues equal to LAPACK's (fp64) on a Gramian with a decaying spectrum."""
+def test_sym_tridiag_of_a_gramian(ctx, d):
+    """The cluster Householder kernel behind the dual-form row path: G = H T H^T to fp32 accuracy with H
+    orthogonal and T tridiagonal, on a Gramian with a decaying spectrum; T has LAPACK's (fp64) eigenvalues."""
     rng = np.random.default_rng(d)
     E = (rng.standard_normal((3000, d)) * np.exp(-np.arange(d) / 40.0)[None, :]) @ np.linalg.qr(rng.standard_normal((d, d)))[0]
     G = (E.T @ E).astype(np.float32)
-    Q, lam, sweeps = ctx.sym_eig(G)
-    print("jacobi sweeps", sweeps)
-    assert 0 < sweeps < 30
+    H, td, ts = ctx.sym_tridiag(G)
+    assert ts[0] == 0
     G64 = 0.5 * (G.astype(np.float64) + G.astype(np.float64).T)
-    Q64 = Q.astype(np.float64)
+    H64 = H.astype(np.float64)
+    T = np.diag(td.astype(np.float64)) + np.diag(ts[1:].astype(np.float64), -1) + np.diag(ts[1:].astype(np.float64), 1)
     scale = np.abs(G64).max()
-    assert np.abs(Q64.T @ Q64 - np.eye(d)).max() < 5e-6
-    assert np.abs(Q64 @ np.diag(lam.astype(np.float64)) @ Q64.T - G64).max() / scale < 5e-6
+    assert np.abs(H64.T @ H64 - np.eye(d)).max() < 5e-6
+    assert np.abs(H64 @ T @ H64.T - G64).max() / scale < 5e-6
     w = np.linalg.eigvalsh(G64)
-    assert np.abs(np.sort(lam.astype(np.float64)) - w).max() / w.max() < 1e-6
+    assert np.abs(np.linalg.eigvalsh(T) - w).max() / w.max() < 1e-6
 
 
 @pytest.mark.parametrize("d", [128, 256])
@@ -314,8 +314,8 @@ def test_sym_eig_of_a_gramian(ctx, d):
     ("safer2", dict(uobs_weight=0.002, reg=0.002, bandwidth=0.18)),
 ])
 def test_dual_form_rows_match_the_oracle(pkg, O, ctx, name, cfg, d):
-    """Rows with at most 128 entries take the dual-form kernel (n x n system in the eigenbasis of the Gramian,
-    rows packed four 32-entry slots to a group).  Histories 1..128 cover every slot count and the packing of
+    """Rows with at most 128 entries take the dual-form kernel (n x n system in the basis that makes the Gramian
+    tridiagonal, rows packed four 32-entry slots to a group).  Histories 1..128 cover every slot count and the packing of
     1 + 3, 2 + 2, 2 + 1 + 1 and 1 + 1 + 1 + 1 slots; after three epochs (trained factors, wider spectrum of G)
     every row must still agree with the fp32 oracle."""
     nu, ni = 900, 700
