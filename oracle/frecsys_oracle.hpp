@@ -213,6 +213,7 @@ inline Mat Gramian(const Mat& E, const float* w = nullptr) {
 
 // selfadjointView<Lower>().rankUpdate(F) with F = d x nb stored as nb rows of
 // d floats (column c of the reference's factor_batch = row c here).
+#ifndef ORACLE_FAST
 inline void RankUpdateLower(real* M, int d, const float* batch, int nb) {
   for (int c = 0; c < nb; ++c) {
     const float* f = batch + (size_t)c * d;
@@ -223,6 +224,38 @@ inline void RankUpdateLower(real* M, int d, const float* batch, int nb) {
     }
   }
 }
+#else
+// TIMING-ONLY build (-DORACLE_FAST, bench.py's CPU legs): the same update with the rows of M tiled by 8, so
+// that a tile stays in L1 across the whole batch instead of streaming the d x d matrix from L2 once per
+// entry (the cache blocking an optimised SYRK like Eigen's does); the inner loop over j is contiguous and
+// vectorised.  Every M[i][j] still adds the entries in batch order.
+inline void RankUpdateLower(real* M, int d, const float* batch, int nb) {
+  constexpr int BI = 8;
+  for (int i0 = 0; i0 < d; i0 += BI) {
+    const int i1 = std::min(d, i0 + BI);
+    for (int c = 0; c < nb; ++c) {
+      const float* f = batch + (size_t)c * d;
+      for (int i = i0; i < i1; ++i) {
+        const real fi = f[i];
+        real* mr = M + (size_t)i * d;
+        for (int j = 0; j <= i; ++j) mr[j] += fi * (real)f[j];
+      }
+    }
+  }
+}
+// dot product with 16 independent partial sums (vectorised without -ffast-math)
+inline real FastDot(const real* a, const real* b, int n) {
+  real acc[16];
+  for (int q = 0; q < 16; ++q) acc[q] = 0;
+  int p = 0;
+  for (; p + 16 <= n; p += 16)
+    for (int q = 0; q < 16; ++q) acc[q] += a[p + q] * b[p + q];
+  real s = 0;
+  for (int q = 0; q < 16; ++q) s += acc[q];
+  for (; p < n; ++p) s += a[p] * b[p];
+  return s;
+}
+#endif
 
 // Eigen::LLT<MatrixXf, Lower>: in-place lower Cholesky reading only the lower
 // triangle, then forward/back substitution.  Returns false if
@@ -231,7 +264,11 @@ inline bool CholeskySolveLower(real* M, int d, real* b) {
   for (int k = 0; k < d; ++k) {
     real* rk = M + (size_t)k * d;
     real x = rk[k];
+#ifdef ORACLE_FAST
+    x -= FastDot(rk, rk, k);
+#else
     for (int p = 0; p < k; ++p) x -= rk[p] * rk[p];
+#endif
     if (!(x > 0)) return false;
     const real lkk = std::sqrt(x);
     rk[k] = lkk;
@@ -239,7 +276,11 @@ inline bool CholeskySolveLower(real* M, int d, real* b) {
     for (int i = k + 1; i < d; ++i) {
       real* ri = M + (size_t)i * d;
       real s = ri[k];
+#ifdef ORACLE_FAST
+      s -= FastDot(ri, rk, k);
+#else
       for (int p = 0; p < k; ++p) s -= ri[p] * rk[p];
+#endif
       ri[k] = s * inv;
     }
   }
@@ -309,6 +350,61 @@ inline void ConjugateGradientLower(const real* M, int d, const real* rhs, real* 
     for (int i = 0; i < d; ++i) absNew += r[i] * z[i];
     const real beta = absNew / absOld;
     for (int i = 0; i < d; ++i) p[i] = z[i] + beta * p[i];
+  }
+}
+
+// Eigen::BiCGSTAB<MatrixXf, DiagonalPreconditioner<float>> on the FULL row-major matrix (SURVEY.md B-5;
+// call sites erm_mf.h:139-145, 198-204): ERM-MF hands it the matrix whose strict upper triangle holds only
+// the Gramian term (rankUpdate writes the lower triangle), so this is NOT the symmetric system LLT solves.
+// Restates Eigen 3.4.0 internal::bicgstab (IterativeLinearSolvers/BiCGSTAB.h): x0 = 0, stop when
+// |r|^2 <= tol^2 |rhs|^2 or after max_it iterations, restart when r became orthogonal to r0.
+inline void BiCGSTABFull(const real* M, int d, const real* rhs, real* x, float tol_in, int max_it) {
+  auto matvec = [&](const real* in, real* out) {
+    for (int i = 0; i < d; ++i) {
+      const real* ri = M + (size_t)i * d;
+      real s = 0;
+      for (int j = 0; j < d; ++j) s += ri[j] * in[j];
+      out[i] = s;
+    }
+  };
+  auto dot = [&](const real* a, const real* b) { real s = 0; for (int i = 0; i < d; ++i) s += a[i] * b[i]; return s; };
+  std::vector<real> r(rhs, rhs + d), r0(rhs, rhs + d), v(d, 0), p(d, 0), y(d), z(d), s(d), t(d), dinv(d);
+  for (int i = 0; i < d; ++i) {
+    x[i] = 0;
+    const real di = M[(size_t)i * d + i];
+    dinv[i] = di != 0 ? (real)1 / di : (real)1;
+  }
+  real r0_sqnorm = dot(r0.data(), r0.data());
+  const real rhs_sqnorm = dot(rhs, rhs);
+  if (rhs_sqnorm == 0) return;
+  real rho = 1, alpha = 1, w = 1;
+  const real tol = (real)tol_in;
+  const real tol2 = tol * tol * rhs_sqnorm;
+  const real eps2 = std::numeric_limits<real>::epsilon() * std::numeric_limits<real>::epsilon();
+  int i = 0, restarts = 0;
+  while (dot(r.data(), r.data()) > tol2 && i < max_it) {
+    const real rho_old = rho;
+    rho = dot(r0.data(), r.data());
+    if (std::abs(rho) < eps2 * r0_sqnorm) {
+      matvec(x, t.data());
+      for (int k = 0; k < d; ++k) r[k] = rhs[k] - t[k];
+      r0 = r;
+      rho = r0_sqnorm = dot(r.data(), r.data());
+      if (restarts++ == 0) i = 0;
+    }
+    const real beta = (rho / rho_old) * (alpha / w);
+    for (int k = 0; k < d; ++k) p[k] = r[k] + beta * (p[k] - w * v[k]);
+    for (int k = 0; k < d; ++k) y[k] = dinv[k] * p[k];
+    matvec(y.data(), v.data());
+    alpha = rho / dot(r0.data(), v.data());
+    for (int k = 0; k < d; ++k) s[k] = r[k] - alpha * v[k];
+    for (int k = 0; k < d; ++k) z[k] = dinv[k] * s[k];
+    matvec(z.data(), t.data());
+    const real tmp = dot(t.data(), t.data());
+    w = tmp > 0 ? dot(t.data(), s.data()) / tmp : (real)0;
+    for (int k = 0; k < d; ++k) x[k] += alpha * y[k] + w * z[k];
+    for (int k = 0; k < d; ++k) r[k] = s[k] - w * t[k];
+    ++i;
   }
 }
 
@@ -572,9 +668,13 @@ class Model {
   }
 
   bool Solve(real* M, int d, real* rhs, real* x) const {
-    if (cfg.use_cg && (cfg.model == kIALS || cfg.model == kSAFER2 || cfg.model == kERMMF)) {
-      // ERM-MF's BiCGSTAB-on-unsymmetrised-matrix (B-5, erm_mf.h:139-145) is not
-      // restated; ERM-MF --use_cg falls to the symmetric CG here.
+    if (cfg.use_cg && cfg.model == kERMMF) {
+      // erm_mf.h:139-145, 198-204: BiCGSTAB on the full matrix, whose strict upper triangle lacks the
+      // rank updates (B-5) -- a different, non-symmetric system than the one LLT<Lower> solves.
+      BiCGSTABFull(M, d, rhs, x, cfg.cg_tol, cfg.cg_max_it);
+      return true;
+    }
+    if (cfg.use_cg && (cfg.model == kIALS || cfg.model == kSAFER2)) {
       ConjugateGradientLower(M, d, rhs, x, cfg.cg_tol, cfg.cg_max_it);
       return true;
     }

@@ -10,8 +10,13 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB = os.path.join(HERE, "libfrecsys_oracle.so")
-STAMP = os.path.join(HERE, ".oracle_build_stamp")
+# FRECSYS_ORACLE_FAST=1 (set by bench.py's CPU legs BEFORE this module is imported) selects the timing-only
+# build: SYRK / Cholesky register-blocked and vectorised like Eigen's, different summation order.  The parity
+# tests never set it.
+FAST = os.environ.get("FRECSYS_ORACLE_FAST", "0") == "1"
+LIB_NAME = "libfrecsys_oracle_fast.so" if FAST else "libfrecsys_oracle.so"
+LIB = os.path.join(HERE, LIB_NAME)
+STAMP = os.path.join(HERE, ".oracle_build_stamp_fast" if FAST else ".oracle_build_stamp")
 
 MODEL_IDS = {"ials": 0, "ialspp": 1, "erm_mf": 2, "cvar_mf": 3, "safer2": 4, "safer2pp": 5}
 
@@ -75,7 +80,7 @@ def _build_locked(sig, force):
           and os.path.getmtime(LIB) >= newest)
     if ok and not force:
         return LIB
-    subprocess.run(["make", "-C", HERE, "-B", "libfrecsys_oracle.so"], check=True,
+    subprocess.run(["make", "-C", HERE, "-B", LIB_NAME], check=True,
                    stdout=subprocess.DEVNULL)
     with open(STAMP, "w") as f:
         f.write(sig)

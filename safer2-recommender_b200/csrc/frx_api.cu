@@ -806,8 +806,15 @@ static int run_rows(frx_model* m, const RowCall& rc_) {
   p.uw = m->cfg.uobs_weight; p.reg = m->cfg.reg; p.reg_exp = m->cfg.reg_exp; p.alpha = m->cfg.alpha;
   p.stepsize = m->cfg.stepsize; p.num_users_total = m->num_users;
   p.status = c->status_dev;
+  // --use_cg: the reference's iterative solvers, with their stopping rule, in the generic kernel
+  if (m->cfg.use_cg && (p.mode == RM_IALS || p.mode == RM_SAFER_U || p.mode == RM_SAFER_V) &&
+      (m->cfg.model == FRX_IALS || m->cfg.model == FRX_SAFER2 || m->cfg.model == FRX_ERM_MF)) {
+    p.solver = m->cfg.model == FRX_ERM_MF ? 2 : 1;
+    p.cg_tol = m->cfg.cg_tol;
+    p.cg_max_it = m->cfg.cg_max_it;
+  }
   static const bool disable_tc = getenv("FRX_DISABLE_TC") != nullptr;
-  if (!disable_tc && row_solve_tc_supported(p)) {
+  if (!disable_tc && p.solver == 0 && row_solve_tc_supported(p)) {
     static const bool tc_debug = getenv("FRX_TC_DEBUG") != nullptr;
     unsigned long long* dbg = nullptr;
     if (tc_debug) {
@@ -892,7 +899,7 @@ static int run_rows(frx_model* m, const RowCall& rc_) {
     }
     return FRX_OK;
   }
-  const size_t per = row_solve_generic_scratch_floats(p.bd);
+  const size_t per = row_solve_generic_scratch_floats(p.bd, p.solver);
   if (per) {
     const int g = row_solve_generic_grid(p.num_rows, c->num_sms);
     int r = c->ensure_row_scratch(per * (size_t)g);

@@ -48,6 +48,11 @@ struct RowParams {
   size_t scratch_stride;
   int use_smem_matrix;
   int* status;  // set non-zero on a non-positive pivot
+  // --use_cg (generic kernel only): 0 LLT, 1 Eigen::ConjugateGradient<Lower> (ials.h:133-138, safer2.h:152-157),
+  // 2 Eigen::BiCGSTAB on the unsymmetrised full matrix (erm_mf.h:139-145, SURVEY B-5)
+  int solver;
+  float cg_tol;
+  int cg_max_it;
   int* work_counter;  // tensor-core row kernel: work queue of the launch (zeroed by the launcher)
   unsigned long long* dbg;  // optional per-phase cycle counters (FRX_TC_DEBUG), else null
   // Long rows (tensor-core path): a row with more than FRX_SPLIT_MIN entries is cut into pieces of
@@ -67,7 +72,7 @@ constexpr int FRX_PIECE = 4096;
 size_t row_solve_tc_piece_floats(int d);  // piece_stride for dimension d
 
 void launch_row_solve_generic(const RowParams& p, cudaStream_t s, int num_sms, long long* launches);
-size_t row_solve_generic_scratch_floats(int bd);  // per-CTA scratch (0 if shared memory suffices)
+size_t row_solve_generic_scratch_floats(int bd, int solver = 0);  // per-CTA scratch (0 if shared memory suffices)
 int row_solve_generic_grid(int num_rows, int num_sms);
 
 // tcgen05 / TMEM path (frx_row_tc.cu): full-dimension solves with d = 128 or 256.

@@ -21,8 +21,8 @@ constexpr int CH = 32;    // history entries staged per chunk
 __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
 
 struct SmemLayout {
-  int dp, chunk_off, qr_off, colk_off, ldiag_off, xv_off, sol_off, mtx_off, total_no_mtx, ntri;
-  __host__ __device__ SmemLayout(int bd, int d) {
+  int dp, chunk_off, qr_off, colk_off, ldiag_off, xv_off, sol_off, cg_off, mtx_off, total_no_mtx, ntri;
+  __host__ __device__ SmemLayout(int bd, int d, int solver = 0) {
     dp = (bd + 3) & ~3;
     int dx = (d + 3) & ~3;
     chunk_off = 0;
@@ -31,7 +31,8 @@ struct SmemLayout {
     ldiag_off = colk_off + dp + 4;
     xv_off = ldiag_off + dp;
     sol_off = xv_off + dx;
-    mtx_off = sol_off + dp;
+    cg_off = sol_off + dp;                          // iterative solvers: 8 work vectors + reduction scratch
+    mtx_off = cg_off + (solver ? 8 * dp + 32 : 0);
     total_no_mtx = mtx_off;
     ntri = ((dp + 1) * (dp + 2)) >> 1;
   }
@@ -48,7 +49,7 @@ __global__ void __launch_bounds__(NT_MAX) row_solve_generic_kernel(RowParams p) 
   const int NT = blockDim.x, NW = NT >> 5;
   extern __shared__ __align__(16) float smem[];
   const int bd = p.bd, d = p.d, cs = p.cs, mode = p.mode;
-  const SmemLayout L(bd, d);
+  const SmemLayout L(bd, d, p.solver);
   const int dp = L.dp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* chunk = smem + L.chunk_off;
@@ -235,6 +236,123 @@ __global__ void __launch_bounds__(NT_MAX) row_solve_generic_kernel(RowParams p) 
       continue;
     }
 
+    if (p.solver != 0) {
+      // ---- --use_cg: the reference's iterative solvers instead of LLT (safer2.h:152-157, ials.h:133-138:
+      // Eigen::ConjugateGradient<MatrixXf, Lower>; erm_mf.h:139-145, 198-204: Eigen::BiCGSTAB on the FULL matrix,
+      // whose strict upper triangle holds only the Gramian term -- SURVEY.md B-5).  Both with the diagonal
+      // preconditioner, x0 = 0 and Eigen's stopping rule |r|^2 < tol^2 |rhs|^2 or max_iterations. ----
+      float* cgv = smem + L.cg_off;
+      float* x_ = sol;
+      float* r_ = cgv;            float* p_ = cgv + dp;      float* z_ = cgv + 2 * dp;  float* t_ = cgv + 3 * dp;
+      float* r0_ = cgv + 4 * dp;  float* v_ = cgv + 5 * dp;  float* y_ = cgv + 6 * dp;  float* s_ = cgv + 7 * dp;
+      float* red = cgv + 8 * dp;
+      const bool full = (p.solver == 2);
+      // strict upper triangle of the reference's full matrix: (weight *) uw * G only (B-2)
+      const float gscale = user_form ? weight * p.uw : p.uw;
+      auto bdot = [&](const float* a, const float* b) -> float {
+        float acc = 0.f;
+        for (int k = tid; k < bd; k += NT) acc = fmaf(a[k], b[k], acc);
+        acc = warp_sum(acc);
+        __syncthreads();
+        if (lane == 0) red[warp] = acc;
+        __syncthreads();
+        float tot = 0.f;
+        for (int wv = 0; wv < NW; ++wv) tot += red[wv];
+        return tot;
+      };
+      auto matvec = [&](const float* in, float* out) {  // callers synchronise before and after
+        for (int i = warp; i < bd; i += NW) {
+          const float* mrow = Mtx + tri(i);
+          float a = 0.f;
+          for (int j = lane; j <= i; j += 32) a = fmaf(mrow[j], in[j], a);
+          if (full) {
+            const float* grow = p.G + (size_t)(cs + i) * d + cs;
+            for (int j = i + 1 + lane; j < bd; j += 32) a = fmaf(gscale * __ldg(grow + j), in[j], a);
+          } else {  // selfadjointView<Lower>
+            for (int j = i + 1 + lane; j < bd; j += 32) a = fmaf(Mtx[tri(j) + i], in[j], a);
+          }
+          a = warp_sum(a);
+          if (lane == 0) out[i] = a;
+        }
+      };
+      auto dinv = [&](int k) -> float { const float dg = Mtx[tri(k) + k]; return dg != 0.f ? 1.f / dg : 1.f; };
+      for (int k = tid; k < bd; k += NT) { x_[k] = 0.f; r_[k] = rhs[k]; r0_[k] = rhs[k]; v_[k] = 0.f; p_[k] = 0.f; }
+      __syncthreads();
+      const float rhs2 = bdot(rhs, rhs);
+      const float tol2 = p.cg_tol * p.cg_tol * rhs2;
+      if (rhs2 != 0.f && !full) {
+        const float threshold = fmaxf(tol2, FLT_MIN);
+        if (!(rhs2 < threshold)) {
+          for (int k = tid; k < bd; k += NT) p_[k] = dinv(k) * r_[k];
+          __syncthreads();
+          float abs_new = bdot(r_, p_);
+          for (int it = 0; it < p.cg_max_it; ++it) {
+            __syncthreads();
+            matvec(p_, t_);
+            __syncthreads();
+            const float alpha = abs_new / bdot(p_, t_);
+            for (int k = tid; k < bd; k += NT) { x_[k] = fmaf(alpha, p_[k], x_[k]); r_[k] = fmaf(-alpha, t_[k], r_[k]); }
+            __syncthreads();
+            const float res2 = bdot(r_, r_);
+            if (res2 < threshold) break;
+            for (int k = tid; k < bd; k += NT) z_[k] = dinv(k) * r_[k];
+            __syncthreads();
+            const float abs_old = abs_new;
+            abs_new = bdot(r_, z_);
+            const float beta = abs_new / abs_old;
+            for (int k = tid; k < bd; k += NT) p_[k] = fmaf(beta, p_[k], z_[k]);
+          }
+        }
+      } else if (rhs2 != 0.f) {
+        float r0_sq = rhs2, rho = 1.f, alpha = 1.f, w = 1.f;
+        const float eps2 = FLT_EPSILON * FLT_EPSILON;
+        int it = 0, restarts = 0;
+        while (it < p.cg_max_it) {
+          if (!(bdot(r_, r_) > tol2)) break;
+          const float rho_old = rho;
+          rho = bdot(r0_, r_);
+          if (fabsf(rho) < eps2 * r0_sq) {  // r became orthogonal to r0: restart from the true residual
+            __syncthreads();
+            matvec(x_, t_);
+            __syncthreads();
+            for (int k = tid; k < bd; k += NT) { const float rr = rhs[k] - t_[k]; r_[k] = rr; r0_[k] = rr; }
+            __syncthreads();
+            rho = r0_sq = bdot(r_, r_);
+            if (restarts++ == 0) it = 0;
+          }
+          const float beta = (rho / rho_old) * (alpha / w);
+          for (int k = tid; k < bd; k += NT) {
+            const float pk = r_[k] + beta * (p_[k] - w * v_[k]);
+            p_[k] = pk;
+            y_[k] = dinv(k) * pk;
+          }
+          __syncthreads();
+          matvec(y_, v_);
+          __syncthreads();
+          alpha = rho / bdot(r0_, v_);
+          for (int k = tid; k < bd; k += NT) {
+            const float sk = r_[k] - alpha * v_[k];
+            s_[k] = sk;
+            z_[k] = dinv(k) * sk;
+          }
+          __syncthreads();
+          matvec(z_, t_);
+          __syncthreads();
+          const float tt = bdot(t_, t_);
+          w = tt > 0.f ? bdot(t_, s_) / tt : 0.f;
+          for (int k = tid; k < bd; k += NT) {
+            x_[k] += alpha * y_[k] + w * z_[k];
+            r_[k] = s_[k] - w * t_[k];
+          }
+          __syncthreads();
+          ++it;
+        }
+      }
+      __syncthreads();
+      for (int k = tid; k < bd; k += NT) p.X[(size_t)xr * d + k] = x_[k];
+      continue;
+    }
+
     // ---- Cholesky of the augmented system (rows 0..dp; row dp carries rhs -> y) -----
     for (int k = 0; k < dp; ++k) {
       float pivot = Mtx[tri(k) + k];
@@ -296,16 +414,16 @@ __global__ void __launch_bounds__(NT_MAX) row_solve_generic_kernel(RowParams p) 
   }
 }
 
-size_t smem_bytes_for(int bd, int d, bool with_matrix) {
-  SmemLayout L(bd, d);
+size_t smem_bytes_for(int bd, int d, bool with_matrix, int solver = 0) {
+  SmemLayout L(bd, d, solver);
   return sizeof(float) * (size_t)(L.total_no_mtx + (with_matrix ? L.ntri : 0));
 }
 constexpr size_t kMaxSmem = 220 * 1024;
 }  // namespace
 
-size_t row_solve_generic_scratch_floats(int bd) {
-  SmemLayout L(bd, bd);
-  if (smem_bytes_for(bd, bd, true) <= kMaxSmem) return 0;
+size_t row_solve_generic_scratch_floats(int bd, int solver) {
+  SmemLayout L(bd, bd, solver);
+  if (smem_bytes_for(bd, bd, true, solver) <= kMaxSmem) return 0;
   return (size_t)((L.ntri + 31) & ~31);
 }
 
@@ -318,9 +436,9 @@ int row_solve_generic_grid(int num_rows, int num_sms) {
 void launch_row_solve_generic(const RowParams& p_in, cudaStream_t s, int num_sms, long long* launches) {
   if (p_in.num_rows <= 0) return;
   RowParams p = p_in;
-  const bool fits = smem_bytes_for(p.bd, p.d, true) <= kMaxSmem;
+  const bool fits = smem_bytes_for(p.bd, p.d, true, p.solver) <= kMaxSmem;
   p.use_smem_matrix = fits ? 1 : 0;
-  const size_t smem = smem_bytes_for(p.bd, p.d, fits);
+  const size_t smem = smem_bytes_for(p.bd, p.d, fits, p.solver);
   int per_sm = (int)((size_t)(224 * 1024) / (smem + 1024));
   if (p.bd >= 96) per_sm = per_sm > 2 ? 2 : per_sm;
   if (per_sm < 1) per_sm = 1;

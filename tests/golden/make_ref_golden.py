@@ -38,6 +38,16 @@ CASES = {
     "safer2pp_d8_e1": ("safer2pp", 8, 1, dict(uobs_weight=0.004, reg=0.004, bandwidth=0.15, block_size=4)),
     "safer2pp_d8_e3": ("safer2pp", 8, 3, dict(uobs_weight=0.004, reg=0.004, bandwidth=0.15, block_size=4)),
     "ials_cg_d8_e1": ("ials", 8, 1, dict(uobs_weight=0.1, reg=0.003, use_cg=1)),
+    # --use_cg: Eigen ConjugateGradient<Lower> (safer2.h:152-157) and ERM-MF's BiCGSTAB on the unsymmetrised
+    # matrix (erm_mf.h:139-145, SURVEY B-5)
+    "safer2_cg_d8_e1": ("safer2", 8, 1, dict(uobs_weight=0.004, reg=0.004, bandwidth=0.15, use_cg=1)),
+    "erm_mf_cg_d8_e1": ("erm_mf", 8, 1, dict(uobs_weight=0.004, reg=0.005, use_cg=1)),
+    "erm_mf_cg_d32_e1": ("erm_mf", 32, 1, dict(uobs_weight=0.004, reg=0.005, use_cg=1)),
+    # d = 128: the tcgen05 row kernels (direct + dual form) and the TMA Gramian; default block_size = 64 (run_model.cc:174)
+    "safer2_d128_e1": ("safer2", 128, 1, dict(uobs_weight=0.004, reg=0.004, bandwidth=0.15)),
+    "ials_d128_e1": ("ials", 128, 1, dict(uobs_weight=0.2, reg=0.006)),
+    "ialspp_d128_b64_e1": ("ialspp", 128, 1, dict(uobs_weight=0.1, reg=0.003, block_size=64)),
+    "safer2pp_d128_b64_e1": ("safer2pp", 128, 1, dict(uobs_weight=0.004, reg=0.004, bandwidth=0.15, block_size=64)),
 }
 
 

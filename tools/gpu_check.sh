@@ -1,9 +1,9 @@
 mkdir -p gpurun_out
-(timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "sym_tridiag or dual_form or tensor_core" -s 2>&1 | tail -60) > gpurun_out/a_tests.log
-tail -25 gpurun_out/a_tests.log
-if grep -q "passed" gpurun_out/a_tests.log && ! grep -q "failed" gpurun_out/a_tests.log; then
-(FRX_TC_DEBUG=1 timeout 200 python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/a_dbg.json) 2> gpurun_out/a_dbg.err
-(timeout 200 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --profile-stages > gpurun_out/a_bench.json) 2> gpurun_out/a_bench.err
-grep "frx wb" gpurun_out/a_dbg.err | tail -3; grep "frx tc" gpurun_out/a_dbg.err | tail -6; cat gpurun_out/a_bench.err | tail -20; python -c "
-import json; d=json.load(open('gpurun_out/a_bench.json')); print(d['ms_per_step'], d['e2e']['ms_per_step'], d['check'])"
-fi
+(timeout 1000 python -m pytest tests -q -m gpu --timeout 180 2>&1 | tail -40) > gpurun_out/c_tests.log
+tail -15 gpurun_out/c_tests.log
+(timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --profile-stages > gpurun_out/c_bench.json) 2> gpurun_out/c_bench.err
+cat gpurun_out/c_bench.err | tail -14; python -c "
+import json; d=json.load(open('gpurun_out/c_bench.json')); print(d['ms_per_step'], d['e2e']['ms_per_step'], d['check'])"
+(timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --profile-stages --dim 128 > gpurun_out/c_bench128.json) 2> gpurun_out/c_bench128.err
+cat gpurun_out/c_bench128.err | tail -14; python -c "
+import json; d=json.load(open('gpurun_out/c_bench128.json')); print(d['ms_per_step'], d['e2e']['ms_per_step'], d['check'])"
