@@ -18,6 +18,7 @@ protected:
     LOG(INFO) << "Weighted Loss: " << s.weighted_loss;  // cvar_mf.h:301-302
     LOG(INFO) << "Mean weights: " << s.mean_weight;     // cvar_mf.h:303
     LOG(INFO) << "Exact Quantile:" << s.xi;             // cvar_mf.h:592
+    if (print_residualstats_) PrintResidualStats(true);  // cvar_mf.h:322-326
     LOG(INFO) << "Xi:" << s.xi;                         // cvar_mf.h:327
   }
 

@@ -15,7 +15,10 @@ public:
   void Initialize(const Dataset& data) { initialize_on_device(data); }  // erm_mf.h:573-587
 
 protected:
-  void after_train() override { LOG(INFO) << "Weighted Loss: " << scalars().weighted_loss; }  // erm_mf.h:277-278
+  void after_train() override {
+    LOG(INFO) << "Weighted Loss: " << scalars().weighted_loss;  // erm_mf.h:277-278
+    if (print_residualstats_) PrintResidualStats(false);       // erm_mf.h:297-300
+  }
 
 private:
   static frx_config make(int dim, float reg, float uw, float stdev, float alpha, bool use_cg, float tol, int max_it) {

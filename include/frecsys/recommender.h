@@ -120,7 +120,10 @@ public:
   }
 
   void SetPrintTrainStats(const bool v) override { print_trainstats_ = v; }
-  void SetPrintResidualStats(const bool v) override { print_residualstats_ = v; }
+  void SetPrintResidualStats(const bool v) override {
+    print_residualstats_ = v;
+    check(frx_model_set_residual_stats(model_, v ? 1 : 0), "frx_model_set_residual_stats");
+  }
   void SetPrintVarStats(const bool v) override { print_varstats_ = v; }
 
   // ials.h:410-412 etc.: the only factor accessor of the reference.
@@ -170,8 +173,22 @@ protected:
     std::snprintf(buf, sizeof buf, "Min: %.3f, Mean: %.3f, Max: %.3f", mn, sum / (float)z.size(), mx);
     LOG(INFO) << buf;
   }
+  // "U residual: .., V residual: ..[, z residual: ..]" of --print_residual_stats (safer2.h:323-328, ials.h:220-223,
+  // ialspp.h:257-260, erm_mf.h:297-300, cvar_mf.h:322-326, safer2pp.h:346-350): norms of the change of U, V and
+  // the dual weights, computed on the device; one line per primal-dual iteration.
+  void PrintResidualStats(bool with_z) const {
+    float r[3 * 64];
+    const int n = frx_model_get_residuals(model_, r, 64);
+    check(n, "frx_model_get_residuals");
+    for (int t = 0; t < n; ++t) {
+      char buf[160];
+      if (with_z) std::snprintf(buf, sizeof buf, "U residual: %.9g, V residual: %.9g, z residual: %.9g", r[3 * t], r[3 * t + 1], r[3 * t + 2]);
+      else std::snprintf(buf, sizeof buf, "U residual: %.9g, V residual: %.9g", r[3 * t], r[3 * t + 1]);
+      LOG(INFO) << buf;
+    }
+  }
   virtual bool stats_after_train() const { return false; }
-  virtual void after_train() {}
+  virtual void after_train() { if (print_residualstats_) PrintResidualStats(false); }  // ials.h:220-223, ialspp.h:257-260
 
   // "Loss=... Loss_observed=..." and "Time=" lines (safer2.h:405-412, ials.h:297-304).
   void PrintLosses(frx_dataset* ds) {

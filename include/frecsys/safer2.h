@@ -38,6 +38,7 @@ protected:
     const Scalars s = scalars();
     LOG(INFO) << "Weighted Loss: " << s.weighted_loss;  // safer2.h:300-301 (last primal-dual iteration)
     if (print_varstats_) PrintVarStats(cfg_.alpha);  // safer2.h:303-319
+    if (print_residualstats_) PrintResidualStats(true);  // safer2.h:323-328
     LOG(INFO) << "Xi:" << s.xi;                         // safer2.h:332
   }
 };

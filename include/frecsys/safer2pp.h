@@ -26,6 +26,7 @@ protected:
     const Scalars s = scalars();
     LOG(INFO) << "Weighted Loss: " << s.weighted_loss;
     if (print_varstats_) PrintVarStats(cfg_.alpha);  // safer2pp.h
+    if (print_residualstats_) PrintResidualStats(true);  // safer2pp.h:346-350
     LOG(INFO) << "Xi:" << s.xi;
   }
 };

@@ -144,6 +144,13 @@ int frx_model_set_state(frx_model* m, const float* z, const float* loss, float x
  * (safer2.h:337-413, ials.h:226-305): out6 = Loss, Loss_observed,
  * Loss_unobserved, Loss_reg, Loss_reg(user), Loss_reg(item). */
 int frx_model_compute_stats(frx_model* m, frx_dataset* train, double* out6);
+/* SetPrintResidualStats(bool) (safer2.h:804-806 and siblings): when on, Train() also records, per primal-dual
+ * iteration, the norms the reference logs as "U residual / V residual / z residual" (safer2.h:323-328,475-478,
+ * 550-553,789-792): |U_new - U_old| over the solved rows, |V_new - V_old|_F, |z_new - z_old|.
+ * frx_model_get_residuals copies up to max_triples triples (U, V, z) of the last Train() and returns their
+ * count; iALS reports 0, 0 (ials.h:363-364) and CVaR-MF 0 for U (cvar_mf.h:472-473) like the reference. */
+int frx_model_set_residual_stats(frx_model* m, int on);
+int frx_model_get_residuals(frx_model* m, float* out, int max_triples);
 /* The SNR indices drawn by the last ComputeXi: [n_iters x n_samples]. */
 int frx_model_last_snr(frx_model* m, int* n_iters, int* n_samples, int* out);
 /* EvaluateDataset(k_list, alpha_list, data=test_tr, eval_by_user=test_te) —

@@ -24,7 +24,7 @@ EXPORTS = [
     "frx_model_destroy", "frx_model_init_factors", "frx_model_set_factors", "frx_model_get_factors", "frx_model_upload_factors",
     "frx_model_initialize", "frx_model_train", "frx_model_stage", "frx_model_get_state",
     "frx_model_set_state", "frx_model_compute_stats", "frx_model_last_snr", "frx_model_evaluate",
-    "frx_context_launch_count", "frx_context_set_profiling", "frx_context_stage_times", "frx_gramian", "frx_sym_tridiag",
+    "frx_context_launch_count", "frx_context_set_profiling", "frx_context_stage_times", "frx_gramian", "frx_sym_tridiag", "frx_model_set_residual_stats", "frx_model_get_residuals",
 ]
 
 
@@ -123,6 +123,8 @@ def lib():
     L.frx_context_stage_times.argtypes = [vp, C.c_char_p, C.c_int, fp, C.c_int]
     L.frx_gramian.argtypes = [vp, fp, C.c_int, C.c_int, fp, fp]
     L.frx_sym_tridiag.argtypes = [vp, fp, C.c_int, fp, fp, fp]
+    L.frx_model_set_residual_stats.argtypes = [vp, C.c_int]
+    L.frx_model_get_residuals.argtypes = [vp, fp, C.c_int]
     _lib = L
     return L
 
@@ -330,6 +332,15 @@ class Model:
         _check(lib().frx_model_compute_stats(self.h, ds.h, out))
         keys = ["loss", "loss_observed", "loss_unobserved", "loss_reg", "loss_reg_user", "loss_reg_item"]
         return dict(zip(keys, list(out)))
+
+    def set_residual_stats(self, on=True):
+        _check(lib().frx_model_set_residual_stats(self.h, 1 if on else 0))
+
+    def residuals(self):
+        """[iterations x 3] U / V / z residual norms of the last train() (--print_residual_stats)."""
+        out = np.zeros(3 * 64, np.float32)
+        n = _check(lib().frx_model_get_residuals(self.h, _fp(out), 64))
+        return out[:3 * n].reshape(n, 3)
 
     def last_snr(self):
         ni, ns = C.c_int(), C.c_int()

@@ -168,6 +168,12 @@ struct frx_model {
   frx_context* ctx = nullptr;
   Basis basisV;    // of the cached item Gramian G and V (user half-steps of SAFER2 / ERM-MF, fold-in evaluation)
   Basis basisTmp;  // of a Gramian computed inside a half-step (iALS)
+  // SetPrintResidualStats (safer2.h:323-328): snapshots of U, V, z taken before the stages that change them and
+  // the squared differences per primal-dual iteration [3 * iterations]: U, V, z
+  bool residual_stats = false;
+  float *snapU = nullptr, *snapV = nullptr, *snapZ = nullptr;
+  double* resid_dev = nullptr;
+  int resid_count = 0;
   bool G_dirty = false;  // V was overwritten from the host: G = V^T V must be recomputed before it is read
   float* early_U_host = nullptr;  // frx_model_train_to_host: where U / V go as soon as their half-step is final
   float* early_V_host = nullptr;
@@ -632,6 +638,7 @@ extern "C" void frx_model_destroy(frx_model* m) {
                    m->scal, m->Uprev, m->pred})
     cudaFree(p);
   cudaFree(m->snr_dev);
+  cudaFree(m->snapU); cudaFree(m->snapV); cudaFree(m->snapZ); cudaFree(m->resid_dev);
   free_basis(m->basisV);
   free_basis(m->basisTmp);
   for (int i = 0; i < 2; ++i) {
@@ -1203,6 +1210,55 @@ static int maybe_download(frx_model* m, frx_dataset* ds, bool item_side) {
 static int maybe_download_U(frx_model* m, frx_dataset* ds) { return maybe_download(m, ds, false); }
 static int maybe_download_V(frx_model* m, frx_dataset* ds) { return maybe_download(m, ds, true); }
 
+// Residual statistics: snapshot(which) before a stage, residual(which, slot) after it.  which: 0 U, 1 V, 2 z.
+static const int kMaxResid = 64;
+static int resid_snapshot(frx_model* m, int which) {
+  if (!m->residual_stats) return FRX_OK;
+  frx_context* c = m->ctx;
+  const size_t d = m->cfg.dim;
+  float** snap = which == 0 ? &m->snapU : which == 1 ? &m->snapV : &m->snapZ;
+  const float* src = which == 0 ? m->U : which == 1 ? m->V : m->z;
+  const size_t n = which == 0 ? (size_t)m->num_users * d : which == 1 ? (size_t)m->num_items * d : (size_t)m->num_users;
+  if (!*snap) CK(cudaMalloc(snap, sizeof(float) * n));
+  if (!m->resid_dev) CK(cudaMalloc(&m->resid_dev, sizeof(double) * 3 * kMaxResid));
+  CK(cudaMemcpyAsync(*snap, src, sizeof(float) * n, cudaMemcpyDeviceToDevice, c->stream));
+  return FRX_OK;
+}
+static int resid_record(frx_model* m, int which, int iter) {
+  if (!m->residual_stats || iter >= kMaxResid) return FRX_OK;
+  frx_context* c = m->ctx;
+  const size_t d = m->cfg.dim;
+  const float* snap = which == 0 ? m->snapU : which == 1 ? m->snapV : m->snapZ;
+  const float* cur = which == 0 ? m->U : which == 1 ? m->V : m->z;
+  const size_t n = which == 0 ? (size_t)m->num_users * d : which == 1 ? (size_t)m->num_items * d : (size_t)m->num_users;
+  launch_sqdiff(cur, snap, n, m->resid_dev + 3 * iter + which, c->stream, c->num_sms, &c->launches);
+  CK(cudaGetLastError());
+  m->resid_count = std::max(m->resid_count, iter + 1);
+  return FRX_OK;
+}
+
+extern "C" int frx_model_set_residual_stats(frx_model* m, int on) {
+  m->residual_stats = on != 0;
+  return FRX_OK;
+}
+
+// U / V / z residual norms of the last Train(), one triple per primal-dual iteration, as the reference logs them
+// (safer2.h:323-328, erm_mf.h:297-300, cvar_mf.h:322-326, ialspp.h:257-260, safer2pp.h:346-350).  iALS reports
+// 0, 0 (its Step returns a constant 0, ials.h:363-364), CVaR-MF 0 for U (cvar_mf.h:472-473).  Returns the count.
+extern "C" int frx_model_get_residuals(frx_model* m, float* out, int max_triples) {
+  frx_context* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  const int n = std::min(m->resid_count, max_triples);
+  if (n <= 0) return 0;
+  std::vector<double> h(3 * (size_t)n);
+  CK(cudaMemcpyAsync(h.data(), m->resid_dev, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 3 * n; ++i) out[i] = (float)std::sqrt(h[i]);
+  if (m->cfg.model == FRX_IALS) for (int i = 0; i < n; ++i) out[3 * i] = out[3 * i + 1] = 0.f;
+  if (m->cfg.model == FRX_CVAR_MF) for (int i = 0; i < n; ++i) out[3 * i] = 0.f;
+  return n;
+}
+
 extern "C" int frx_model_train(frx_model* m, frx_dataset* ds) {
   frx_context* c = m->ctx;
   CK(cudaSetDevice(c->device));
@@ -1210,14 +1266,23 @@ extern "C" int frx_model_train(frx_model* m, frx_dataset* ds) {
     return fail(FRX_ERR_ARG, "dataset ids exceed the model's num_users/num_items");
   c->timers_used = 0;
   RC(refresh_item_gramian(m));
+  m->resid_count = 0;
+  if (m->residual_stats) {
+    if (!m->resid_dev) CK(cudaMalloc(&m->resid_dev, sizeof(double) * 3 * kMaxResid));
+    CK(cudaMemsetAsync(m->resid_dev, 0, sizeof(double) * 3 * kMaxResid, c->stream));
+  }
   const int d = m->cfg.dim, B = m->cfg.block_size;
   if (c->world > 1 && m->is_pp())
     return fail(FRX_ERR_ARG, "iALS++ / SAFER2++ are single-GPU in this build (the tuple-indexed prediction cache is not sharded)");
   switch (m->cfg.model) {
     case FRX_IALS:  // ials.h:187-224
+      RC(resid_snapshot(m, 0));
       RC(stage_ials_step(m, ds, true, m->U, nullptr, nullptr));
+      RC(resid_record(m, 0, 0));
       RC(maybe_download_U(m, ds));
+      RC(resid_snapshot(m, 1));
       RC(stage_ials_step(m, ds, false, m->V, nullptr, nullptr));
+      RC(resid_record(m, 1, 0));
       RC(maybe_download_V(m, ds));
       RC(stage_item_gramian(m));  // ComputeUserLoss recomputes the Gramian, ials.h:371
       RC(stage_user_loss(m, ds, m->G, nullptr));
@@ -1225,27 +1290,39 @@ extern "C" int frx_model_train(frx_model* m, frx_dataset* ds) {
     case FRX_IALSPP:  // ialspp.h:208-261
       RC(ensure_pred(m, ds->num_tuples));
       RC(stage_predict(m, &ds->by_user, m->U, nullptr));
+      RC(resid_snapshot(m, 0));
+      RC(resid_snapshot(m, 1));
       for (int start = 0; start < d; start += B) {
         const int end = std::min(start + B, d);
         RC(stage_block(m, &ds->by_user, true, m->U, nullptr, start, end, false, nullptr));
         RC(stage_block(m, &ds->by_item, false, m->V, nullptr, start, end, false, nullptr));
       }
+      RC(resid_record(m, 0, 0));  // sum over the blocks of |delta|^2 = |U_new - U_old|^2 (ialspp.h:218-259)
+      RC(resid_record(m, 1, 0));
       break;
     case FRX_ERM_MF:  // erm_mf.h:257-301
+      RC(resid_snapshot(m, 0));
       RC(stage_step_u(m, ds));
+      RC(resid_record(m, 0, 0));
       RC(maybe_download_U(m, ds));
+      RC(resid_snapshot(m, 1));
       RC(stage_step_v(m, ds, m->U));
+      RC(resid_record(m, 1, 0));
       RC(maybe_download_V(m, ds));
       RC(stage_item_gramian(m));
       RC(stage_user_loss(m, ds, m->G, nullptr));
       RC(stage_means(m));
       break;
     case FRX_CVAR_MF:  // cvar_mf.h:276-330
+      RC(resid_snapshot(m, 2));
       RC(stage_weights(m));
+      RC(resid_record(m, 2, 0));
       CK(cudaMemcpyAsync(m->Uprev, m->U, sizeof(float) * (size_t)m->num_users * d, cudaMemcpyDeviceToDevice,
                          c->stream));  // cvar_mf.h:282
       RC(stage_step_u(m, ds));
+      RC(resid_snapshot(m, 1));
       RC(stage_step_v(m, ds, m->Uprev));
+      RC(resid_record(m, 1, 0));
       RC(stage_item_gramian(m));
       RC(stage_user_loss(m, ds, m->G, nullptr));
       RC(stage_means(m));
@@ -1253,10 +1330,16 @@ extern "C" int frx_model_train(frx_model* m, frx_dataset* ds) {
       break;
     case FRX_SAFER2:  // safer2.h:266-334
       for (int t = 0; t < m->cfg.pd_iterations; ++t) {
+        RC(resid_snapshot(m, 2));
         RC(stage_weights(m));
+        RC(resid_record(m, 2, t));
+        RC(resid_snapshot(m, 0));
         RC(stage_step_u(m, ds));
+        RC(resid_record(m, 0, t));
         if (t == m->cfg.pd_iterations - 1) RC(maybe_download_U(m, ds));
+        RC(resid_snapshot(m, 1));
         RC(stage_step_v(m, ds, m->U));
+        RC(resid_record(m, 1, t));
         if (t == m->cfg.pd_iterations - 1) RC(maybe_download_V(m, ds));
         RC(stage_item_gramian(m));
         RC(stage_user_loss(m, ds, m->G, nullptr));
@@ -1268,12 +1351,18 @@ extern "C" int frx_model_train(frx_model* m, frx_dataset* ds) {
       RC(ensure_pred(m, ds->num_tuples));
       RC(stage_predict(m, &ds->by_user, m->U, nullptr));
       for (int t = 0; t < m->cfg.pd_iterations; ++t) {
+        RC(resid_snapshot(m, 2));
         RC(stage_weights(m));
+        RC(resid_record(m, 2, t));
+        RC(resid_snapshot(m, 0));
+        RC(resid_snapshot(m, 1));
         for (int start = 0; start < d; start += B) {
           const int end = std::min(start + B, d);
           RC(stage_block(m, &ds->by_user, true, m->U, nullptr, start, end, true, m->z));
           RC(stage_block(m, &ds->by_item, false, m->V, nullptr, start, end, true, nullptr));
         }
+        RC(resid_record(m, 0, t));
+        RC(resid_record(m, 1, t));
         RC(stage_item_gramian(m));
         RC(stage_user_loss(m, ds, m->G, m->pred));
         RC(stage_means(m));

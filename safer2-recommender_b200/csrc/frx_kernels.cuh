@@ -67,8 +67,10 @@ struct RowParams {
   float* piece_scratch;    // [num_pieces][piece_stride]: lower 32x32 chunks (row-major), then the rhs partial
   size_t piece_stride;
 };
-constexpr int FRX_SPLIT_MIN = 8192;
-constexpr int FRX_PIECE = 4096;
+// (The piece length also bounds the accumulation chain inside the tensor cores, whose fp32 accumulator rounds
+// toward zero: 128 MMA steps per TMEM pass keep that bias near 4e-6; the pieces are added with IEEE fp32 adds.)
+constexpr int FRX_SPLIT_MIN = 2048;
+constexpr int FRX_PIECE = 1024;
 size_t row_solve_tc_piece_floats(int d);  // piece_stride for dimension d
 
 void launch_row_solve_generic(const RowParams& p, cudaStream_t s, int num_sms, long long* launches);
@@ -199,6 +201,8 @@ void launch_norm_weights(const float* z, const float* hist_size, int n, float* o
                          long long* launches);
 
 void launch_fill(float* p, size_t n, float v, cudaStream_t s, long long* launches);
+// *out += sum (a[i] - b[i])^2 (double); residual statistics (safer2.h:475-478, 550-553, 789-792)
+void launch_sqdiff(const float* a, const float* b, size_t n, double* out, cudaStream_t s, int num_sms, long long* launches);
 
 // Evaluation (recommender.h:78-199): scores = Ut * V^T tile by tile, history
 // mask, per-user top-k, Recall/NDCG.

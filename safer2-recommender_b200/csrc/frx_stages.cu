@@ -658,6 +658,18 @@ __global__ void norm_weights_kernel(const float* __restrict__ z, const float* __
   const int u = blockIdx.x * blockDim.x + threadIdx.x;
   if (u < n) out[u] = z[u] / hs[u];
 }
+// sum (a - b)^2 in double -> *out (atomic: a diagnostic, the order of the partial sums is not fixed)
+__global__ void __launch_bounds__(256) sqdiff_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n,
+                                                     double* __restrict__ out) {
+  __shared__ double sh[33];
+  double s = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double dlt = (double)a[i] - (double)b[i];
+    s += dlt * dlt;
+  }
+  s = block_sum_d(s, sh);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
 __global__ void fill_kernel(float* p, size_t n, float v) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -787,6 +799,14 @@ void launch_hist_and_item_reg(const int* uptr, int num_users_ds, float* hist_siz
 void launch_norm_weights(const float* z, const float* hist_size, int n, float* out, cudaStream_t s,
                          long long* launches) {
   norm_weights_kernel<<<(n + 255) / 256, 256, 0, s>>>(z, hist_size, n, out);
+  if (launches) ++*launches;
+}
+
+void launch_sqdiff(const float* a, const float* b, size_t n, double* out, cudaStream_t s, int num_sms, long long* launches) {
+  if (n == 0) return;
+  size_t g = (n + 255) / 256;
+  if (g > (size_t)num_sms * 8) g = (size_t)num_sms * 8;
+  sqdiff_kernel<<<(unsigned)g, 256, 0, s>>>(a, b, n, out);
   if (launches) ++*launches;
 }
 

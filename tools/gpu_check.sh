@@ -1,9 +1,6 @@
 mkdir -p gpurun_out
-(timeout 1000 python -m pytest tests -q -m gpu --timeout 180 2>&1 | tail -40) > gpurun_out/c_tests.log
-tail -15 gpurun_out/c_tests.log
+(timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 400 -s -k "bench_configuration or long_rows" 2>&1 | grep -v "^    \|^$" | tail -30) > gpurun_out/d_tests.log
+cat gpurun_out/d_tests.log
 (timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --profile-stages > gpurun_out/c_bench.json) 2> gpurun_out/c_bench.err
 cat gpurun_out/c_bench.err | tail -14; python -c "
 import json; d=json.load(open('gpurun_out/c_bench.json')); print(d['ms_per_step'], d['e2e']['ms_per_step'], d['check'])"
-(timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --profile-stages --dim 128 > gpurun_out/c_bench128.json) 2> gpurun_out/c_bench128.err
-cat gpurun_out/c_bench128.err | tail -14; python -c "
-import json; d=json.load(open('gpurun_out/c_bench128.json')); print(d['ms_per_step'], d['e2e']['ms_per_step'], d['check'])"
