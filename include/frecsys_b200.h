@@ -72,7 +72,9 @@ void* frx_context_stream(frx_context* ctx);
  * rank 0 calls frx_comm_unique_id and ships the 128 bytes to every rank. */
 int frx_comm_unique_id(void* out128);
 int frx_context_init_comm(frx_context* ctx, int rank, int world_size, const void* unique_id128);
-/* Host-only: the contiguous row ranges the ranks own, balanced on sum(history length + row_unit);
+/* Host-only: the contiguous row ranges the ranks own, balanced on sum(history length + row_unit) over the non-empty
+ * rows; row_unit < 0 selects the built-in cost model of frx_dataset_create (direct rows: length + 480, rows of at
+ * most 128 entries -- the dual-form kernel -- a flat 150);
  * ptr[nrows+1] is a CSR row pointer, rank_begin receives world+1 entries. */
 int frx_partition_rows(const int* ptr, int nrows, int world, int row_unit, int* rank_begin);
 

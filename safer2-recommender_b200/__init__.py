@@ -201,7 +201,7 @@ class Context:
             self.h = None
 
 
-def partition_rows(ptr, world, row_unit=480):
+def partition_rows(ptr, world, row_unit=-1):
     """Row ranges per rank for the row-sharded epoch (host-only; mirrors what frx_dataset_create uses)."""
     ptr = np.ascontiguousarray(ptr, np.int32)
     out = np.zeros(world + 1, np.int32)

@@ -50,6 +50,35 @@ struct frx_context {
   bool own_stream = false;
   cudaStream_t copy_stream = nullptr;  // device->host copies that overlap the rest of an epoch (frx_model_train_to_host)
   cudaEvent_t copy_ev = nullptr;
+  // Side stream of the dual-form row path: tridiagonalisation + rotation of the Gramian basis, per-row factors,
+  // group kernel and the back rotation run beside the direct row kernel of the main stream (the persistent CTAs of
+  // the two kernels cannot share an SM, so the dual-form CTAs fill the SMs the direct kernel's queue drains).
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+  bool side_pending = false;  // work on the side stream that the main stream has not waited for yet
+  int ensure_side() {
+    if (side_stream) return 0;
+    CK(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&join_ev, cudaEventDisableTiming));
+    return 0;
+  }
+  // side stream continues after everything enqueued on the main stream so far
+  int fork_side() {
+    int rc = ensure_side();
+    if (rc) return rc;
+    CK(cudaEventRecord(fork_ev, stream));
+    CK(cudaStreamWaitEvent(side_stream, fork_ev, 0));
+    return 0;
+  }
+  // main stream continues after everything enqueued on the side stream so far
+  int join_side() {
+    if (!side_pending) return 0;
+    CK(cudaEventRecord(join_ev, side_stream));
+    CK(cudaStreamWaitEvent(stream, join_ev, 0));
+    side_pending = false;
+    return 0;
+  }
   int num_sms = 148;
   long long launches = 0;
   float* gram_ws = nullptr;
@@ -156,11 +185,13 @@ struct frx_dataset {
 struct Basis {
   float *H = nullptr, *HT = nullptr, *tdiag = nullptr, *tsub = nullptr, *Et = nullptr;
   size_t et_rows = 0;
-  bool valid = false;
+  bool valid = false;           // enqueued on the side stream for the current G / E
+  cudaEvent_t done = nullptr;   // recorded on the side stream after the rotation
 };
 
 static void free_basis(Basis& b) {
   cudaFree(b.H); cudaFree(b.HT); cudaFree(b.tdiag); cudaFree(b.tsub); cudaFree(b.Et);
+  if (b.done) cudaEventDestroy(b.done);
   b = Basis();
 }
 
@@ -245,11 +276,15 @@ extern "C" void frx_context_destroy(frx_context* c) {
   cudaFree(c->status_dev);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->copy_ev) cudaEventDestroy(c->copy_ev);
+  if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); }
+  if (c->fork_ev) cudaEventDestroy(c->fork_ev);
+  if (c->join_ev) cudaEventDestroy(c->join_ev);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
 
 extern "C" int frx_context_sync(frx_context* c) {
+  { const int rc_ = c->join_side(); if (rc_) return rc_; }
   CK(cudaStreamSynchronize(c->stream));
   int st = 0;
   CK(cudaMemcpyAsync(&st, c->status_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -322,15 +357,28 @@ extern "C" int frx_context_init_comm(frx_context* c, int rank, int world, const 
 // d x d factorisation, in units of history entries.
 static const int kRowUnit = 480;  // d = 256 tensor-core kernel: ~62K cycles fixed vs ~128 cycles per history entry
 
-// Contiguous row ranges balanced on sum(history length + row_unit).  Pure host code (no GPU needed).
+// Contiguous row ranges balanced on the cost of a row in units of history entries: history length + row_unit for
+// a row of the direct d x d kernel, a flat short_unit for a row of at most FRX_WB_MAX entries (dual-form kernel:
+// its cost is the n x n factorisation of a 32..128-entry group, nearly independent of n).  row_unit < 0 keeps the
+// built-in constants.  Pure host code (no GPU needed).
+static const int kShortUnit = 150;  // ~19K cycles per dual-form row vs ~128 cycles per history entry
 extern "C" int frx_partition_rows(const int* ptr, int nrows, int world, int row_unit, int* rank_begin) {
-  if (!ptr || !rank_begin || nrows < 0 || world < 1 || row_unit < 0) return fail(FRX_ERR_ARG, "bad partition arguments");
+  if (!ptr || !rank_begin || nrows < 0 || world < 1) return fail(FRX_ERR_ARG, "bad partition arguments");
+  const bool builtin = row_unit < 0;
+  if (builtin) row_unit = kRowUnit;
+  auto cost = [&](int r) -> long long {
+    const int n = ptr[r + 1] - ptr[r];
+    if (n == 0) return 0;
+    return (builtin && n <= FRX_WB_MAX) ? kShortUnit : (long long)n + row_unit;
+  };
   for (int k = 0; k <= world; ++k) rank_begin[k] = nrows;
   rank_begin[0] = 0;
-  const long long total = (long long)(ptr[nrows] - ptr[0]) + (long long)nrows * row_unit;
+  long long total = 0;
+  for (int r = 0; r < nrows; ++r) total += cost(r);
+  long long done = 0;
   int k = 1;
   for (int r = 0; r < nrows && k < world; ++r) {
-    const long long done = (long long)(ptr[r + 1] - ptr[0]) + (long long)(r + 1) * row_unit;
+    done += cost(r);
     while (k < world && done * world >= total * k) rank_begin[k++] = r + 1;
   }
   return FRX_OK;
@@ -351,7 +399,7 @@ static int finish_csr(frx_context* c, Csr& m, const int* cost_other_dim) {
   CK(cudaStreamSynchronize(c->stream));
   // Row-id ranges per rank; rank k owns [rank_begin[k], rank_begin[k+1]).
   m.rank_begin.assign(c->world + 1, m.nrows);
-  frx_partition_rows(m.h_ptr.data(), m.nrows, c->world, kRowUnit, m.rank_begin.data());
+  frx_partition_rows(m.h_ptr.data(), m.nrows, c->world, -1, m.rank_begin.data());
   std::vector<int> order;
   m.distinct = 0;
   for (int r = 0; r < m.nrows; ++r)
@@ -633,6 +681,7 @@ extern "C" int frx_model_create(frx_context* c, const frx_config* cfg, int num_u
 extern "C" void frx_model_destroy(frx_model* m) {
   if (!m) return;
   cudaSetDevice(m->ctx->device);
+  m->ctx->join_side();
   cudaStreamSynchronize(m->ctx->stream);
   for (float* p : {m->U, m->V, m->G, m->Gz, m->z, m->loss, m->hist_size, m->norm_w, m->quad, m->item_reg,
                    m->scal, m->Uprev, m->pred})
@@ -650,6 +699,7 @@ extern "C" void frx_model_destroy(frx_model* m) {
 
 extern "C" int frx_model_set_factors(frx_model* m, const float* U, const float* V) {
   frx_context* c = m->ctx;
+  { const int jrc_ = c->join_side(); if (jrc_) return jrc_; }
   const size_t d = m->cfg.dim;
   if (U) CK(cudaMemcpyAsync(m->U, U, sizeof(float) * m->num_users * d, cudaMemcpyHostToDevice, c->stream));
   if (V) CK(cudaMemcpyAsync(m->V, V, sizeof(float) * m->num_items * d, cudaMemcpyHostToDevice, c->stream));
@@ -658,6 +708,7 @@ extern "C" int frx_model_set_factors(frx_model* m, const float* U, const float* 
 
 extern "C" int frx_model_upload_factors(frx_model* m, const float* U, const float* V) {
   frx_context* c = m->ctx;
+  { const int jrc_ = c->join_side(); if (jrc_) return jrc_; }
   CK(cudaSetDevice(c->device));
   const size_t d = m->cfg.dim;
   if (U) CK(cudaMemcpyAsync(m->U, U, sizeof(float) * m->num_users * d, cudaMemcpyHostToDevice, c->stream));
@@ -699,6 +750,7 @@ extern "C" int frx_model_get_factors(frx_model* m, float* U, float* V) {
 // NVLink.  With one rank these are frx_model_upload_factors / frx_model_get_factors.
 extern "C" int frx_model_upload_factors_sharded(frx_model* m, frx_dataset* train, const float* U, const float* V) {
   frx_context* c = m->ctx;
+  { const int jrc_ = c->join_side(); if (jrc_) return jrc_; }
   CK(cudaSetDevice(c->device));
   if (c->world <= 1) return frx_model_upload_factors(m, U, V);
   const size_t d = m->cfg.dim;
@@ -766,7 +818,8 @@ struct RowCall {
   const Basis* basis = nullptr;  // eigenbasis of G with E rotated into it, or null: no dual-form path
 };
 
-// G = H T H^T and Et = E * H on the context stream.
+// G = H T H^T and Et = E * H, enqueued on the SIDE stream after everything the main stream holds so far (G and E
+// are final there); consumers run on the side stream too (run_rows), the main stream joins after them.
 static int compute_basis(frx_model* m, Basis& b, const float* G, const float* E, int rows) {
   frx_context* c = m->ctx;
   const size_t d = m->cfg.dim;
@@ -775,21 +828,23 @@ static int compute_basis(frx_model* m, Basis& b, const float* G, const float* E,
     CK(cudaMalloc(&b.HT, sizeof(float) * d * d));
     CK(cudaMalloc(&b.tdiag, sizeof(float) * d));
     CK(cudaMalloc(&b.tsub, sizeof(float) * d));
+    CK(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
   }
   if (b.et_rows < (size_t)rows) {
+    RC0(c->join_side());
+    CK(cudaStreamSynchronize(c->stream));  // nobody reads the old buffer any more
     cudaFree(b.Et);
     b.Et = nullptr;
     CK(cudaMalloc(&b.Et, sizeof(float) * (size_t)rows * d));
     b.et_rows = rows;
   }
-  c->stage_begin("tridiag");
-  if (launch_sym_tridiag(G, (int)d, b.H, b.HT, b.tdiag, b.tsub, c->stream, &c->launches) != 0)
+  RC0(c->fork_side());
+  if (launch_sym_tridiag(G, (int)d, b.H, b.HT, b.tdiag, b.tsub, c->side_stream, &c->launches) != 0)
     return fail(FRX_ERR_CUDA, "launch of sym_tridiag_kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
-  c->stage_end();
-  c->stage_begin("rotate");
-  launch_rows_gemm(E, rows, (int)d, b.H, b.Et, nullptr, nullptr, c->stream, &c->launches);
-  c->stage_end();
+  launch_rows_gemm(E, rows, (int)d, b.H, b.Et, nullptr, nullptr, c->side_stream, &c->launches);
   CK(cudaGetLastError());
+  CK(cudaEventRecord(b.done, c->side_stream));
+  c->side_pending = true;
   b.valid = true;
   return FRX_OK;
 }
@@ -833,34 +888,10 @@ static int run_rows(frx_model* m, const RowCall& rc_) {
     // rows with at most FRX_WB_MAX entries go to the dual-form kernel when the eigenbasis of G is at hand
     const bool use_wb = rc_.basis && rc_.basis->valid && rc_.rows->wb_num_groups > 0 && row_solve_wb_supported(p);
     const int direct_rows = use_wb ? rc_.rows->num_direct : rc_.rows->num_order;
-    p.num_rows = direct_rows;
-    if (rc_.rows->num_pieces > 0 && !no_split) {
-      // first launch: partial sums of the pieces of the long rows
-      p.piece_stride = row_solve_tc_piece_floats(p.d);
-      int r = c->ensure_row_scratch(p.piece_stride * (size_t)rc_.rows->num_pieces);
-      if (r) return r;
-      p.piece_scratch = c->row_scratch;
-      p.piece_row = rc_.rows->piece_row; p.piece_off = rc_.rows->piece_off; p.row_piece0 = rc_.rows->row_piece0;
-      p.num_pieces = rc_.rows->num_pieces;
-      p.piece_mode = 1;
-      p.work_counter = c->wb_counter + 1;
-      launch_row_solve_tc(p, c->stream, c->num_sms, &c->launches);
-      CK(cudaGetLastError());
-      // second launch: the long rows, each started from the sum of its pieces
-      p.piece_mode = 2;
-      p.num_rows = rc_.rows->num_long;
-      p.work_counter = c->wb_counter + 2;
-      launch_row_solve_tc(p, c->stream, c->num_sms, &c->launches);
-      CK(cudaGetLastError());
-      // the ordinary rows follow
-      p.piece_mode = 0;
-      p.order = rc_.rows->order + rc_.rows->num_long;
-      p.num_rows = direct_rows - rc_.rows->num_long;
-    }
-    p.work_counter = c->wb_counter + 3;
-    launch_row_solve_tc(p, c->stream, c->num_sms, &c->launches);
-    CK(cudaGetLastError());
+    int direct_sms = c->num_sms;
     if (use_wb) {
+      // dual-form rows on the side stream (ordered after the basis there and after the main stream's work so far)
+      RC0(c->fork_side());
       const int nwb = rc_.rows->num_order - rc_.rows->num_direct;
       int r = c->ensure_wb_scratch((size_t)3 * nwb * p.d);
       if (r) return r;
@@ -875,24 +906,59 @@ static int run_rows(frx_model* m, const RowCall& rc_) {
       q.lsub = c->wb_scratch + (size_t)nwb * p.d;
       q.rsd = c->wb_scratch + (size_t)2 * nwb * p.d;
       q.counter = c->wb_counter;
-      p.order = rc_.rows->order;
-      p.num_rows = rc_.rows->num_order;
-      if (tc_debug) CK(cudaMemsetAsync(dbg, 0, 16 * sizeof(unsigned long long), c->stream));
-      launch_row_solve_wb(p, q, nwb, c->stream, c->num_sms, &c->launches);
+      RowParams pw = p;
+      pw.order = rc_.rows->order;
+      pw.num_rows = rc_.rows->num_order;
+      if (tc_debug) CK(cudaMemsetAsync(dbg, 0, 16 * sizeof(unsigned long long), c->side_stream));
+      launch_row_solve_wb(pw, q, nwb, c->side_stream, c->num_sms, &c->launches);
       CK(cudaGetLastError());
       if (tc_debug) {
         unsigned long long h[16];
-        CK(cudaMemcpyAsync(h, dbg, sizeof h, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaMemcpyAsync(h, dbg, sizeof h, cudaMemcpyDeviceToHost, c->side_stream));
+        CK(cudaStreamSynchronize(c->side_stream));
         const double g = (double)q.num_groups;
         fprintf(stderr, "[frx wb] mode=%d groups=%d rows=%d | cycles/group (summed over SMs): solver set0: wait=%.0f chol=%.0f backsub=%.0f gather+sweeps=%.0f (x3 sets) | mma warp: wait_slot=%.0f wait_stage=%.0f issue=%.0f ring=%.0f\n",
                 p.mode, q.num_groups, nwb, 3 * h[0] / g, 3 * h[1] / g, 3 * h[2] / g, 3 * h[3] / g, h[4] / g, h[5] / g, h[6] / g, h[7] / g);
-        CK(cudaMemsetAsync(dbg, 0, 16 * sizeof(unsigned long long), c->stream));
+        CK(cudaMemsetAsync(dbg, 0, 16 * sizeof(unsigned long long), c->side_stream));
+        CK(cudaStreamSynchronize(c->side_stream));
       }
       // back to the original basis: X[row] = xt * H^T
-      launch_rows_gemm(c->wb_scratch, nwb, p.d, rc_.basis->HT, p.X, q.wb_rows, p.xmap, c->stream, &c->launches);
+      launch_rows_gemm(c->wb_scratch, nwb, p.d, rc_.basis->HT, p.X, q.wb_rows, p.xmap, c->side_stream, &c->launches);
       CK(cudaGetLastError());
+      c->side_pending = true;
+      // While the 8-CTA cluster of the tridiagonalisation is still running it needs its SMs: the direct kernel's
+      // work queue does not care how many CTAs serve it.
+      if (cudaEventQuery(rc_.basis->done) != cudaSuccess) direct_sms = std::max(8, c->num_sms - 8);
+      (void)cudaGetLastError();
     }
+    p.num_rows = direct_rows;
+    if (rc_.rows->num_pieces > 0 && !no_split) {
+      // first launch: partial sums of the pieces of the long rows
+      p.piece_stride = row_solve_tc_piece_floats(p.d);
+      int r = c->ensure_row_scratch(p.piece_stride * (size_t)rc_.rows->num_pieces);
+      if (r) return r;
+      p.piece_scratch = c->row_scratch;
+      p.piece_row = rc_.rows->piece_row; p.piece_off = rc_.rows->piece_off; p.row_piece0 = rc_.rows->row_piece0;
+      p.num_pieces = rc_.rows->num_pieces;
+      p.piece_mode = 1;
+      p.work_counter = c->wb_counter + 1;
+      launch_row_solve_tc(p, c->stream, direct_sms, &c->launches);
+      CK(cudaGetLastError());
+      // second launch: the long rows, each started from the sum of its pieces
+      p.piece_mode = 2;
+      p.num_rows = rc_.rows->num_long;
+      p.work_counter = c->wb_counter + 2;
+      launch_row_solve_tc(p, c->stream, direct_sms, &c->launches);
+      CK(cudaGetLastError());
+      // the ordinary rows follow
+      p.piece_mode = 0;
+      p.order = rc_.rows->order + rc_.rows->num_long;
+      p.num_rows = direct_rows - rc_.rows->num_long;
+    }
+    p.work_counter = c->wb_counter + 3;
+    launch_row_solve_tc(p, c->stream, direct_sms, &c->launches);
+    CK(cudaGetLastError());
+    if (use_wb) RC0(c->join_side());
     if (tc_debug) {
       unsigned long long h[16];
       CK(cudaMemcpyAsync(h, dbg, sizeof h, cudaMemcpyDeviceToHost, c->stream));
@@ -933,6 +999,7 @@ static int run_rows_sharded(frx_model* m, const RowCall& rc_) {
 }
 
 static int stage_item_gramian(frx_model* m) {
+  RC0(m->ctx->join_side());  // a basis computation of the previous G may still be reading it
   m->ctx->stage_begin("gramian_V");
   int rc = gramian_into(m, m->V, m->num_items, 0, m->cfg.dim, 0, m->cfg.dim, nullptr, m->G);
   m->ctx->stage_end();
@@ -1064,6 +1131,15 @@ static int stage_xi_exact(frx_model* m) {
   return FRX_OK;
 }
 
+// The next user half-step (and the fold-in evaluation) reads the basis of the item Gramian that has just been
+// computed: start it on the side stream now, under the loss / xi stages and the direct rows of the next epoch.
+static int prefetch_item_basis(frx_model* m, frx_dataset* ds) {
+  if (ds->by_user.wb_num_groups <= 0) return FRX_OK;
+  int brc;
+  item_basis(m, &brc);
+  return brc;
+}
+
 // StepU of SAFER2 / ERM-MF (safer2.h:437-490) on the model's own users.
 static int stage_step_u(frx_model* m, frx_dataset* ds) {
   const Basis* basis = nullptr;
@@ -1160,6 +1236,7 @@ static int stage_predict(frx_model* m, const Csr* rows, const float* U, const in
 
 extern "C" int frx_model_initialize(frx_model* m, frx_dataset* ds) {
   frx_context* c = m->ctx;
+  { const int jrc_ = c->join_side(); if (jrc_) return jrc_; }
   CK(cudaSetDevice(c->device));
   if (m->is_ials_family()) return FRX_OK;  // run_model.cc:246-257
   if (ds->by_user.nrows > m->num_users || ds->by_item.nrows > m->num_items)
@@ -1310,6 +1387,7 @@ extern "C" int frx_model_train(frx_model* m, frx_dataset* ds) {
       RC(resid_record(m, 1, 0));
       RC(maybe_download_V(m, ds));
       RC(stage_item_gramian(m));
+      RC(prefetch_item_basis(m, ds));
       RC(stage_user_loss(m, ds, m->G, nullptr));
       RC(stage_means(m));
       break;
@@ -1342,6 +1420,7 @@ extern "C" int frx_model_train(frx_model* m, frx_dataset* ds) {
         RC(resid_record(m, 1, t));
         if (t == m->cfg.pd_iterations - 1) RC(maybe_download_V(m, ds));
         RC(stage_item_gramian(m));
+        RC(prefetch_item_basis(m, ds));
         RC(stage_user_loss(m, ds, m->G, nullptr));
         RC(stage_means(m));
       }
@@ -1394,6 +1473,7 @@ extern "C" int frx_model_train_to_host(frx_model* m, frx_dataset* ds, float* U, 
 
 extern "C" int frx_model_stage(frx_model* m, frx_dataset* ds, int stage) {
   frx_context* c = m->ctx;
+  { const int jrc_ = c->join_side(); if (jrc_) return jrc_; }
   CK(cudaSetDevice(c->device));
   RC(refresh_item_gramian(m));
   const int d = m->cfg.dim;
@@ -1478,6 +1558,7 @@ extern "C" int frx_model_save(frx_model* m, const char* path) {
 
 extern "C" int frx_model_load(frx_model* m, const char* path) {
   frx_context* c = m->ctx;
+  { const int jrc_ = c->join_side(); if (jrc_) return jrc_; }
   CK(cudaSetDevice(c->device));
   FILE* f = fopen(path, "rb");
   if (!f) return fail(FRX_ERR_ARG, "cannot open %s", path);
@@ -1664,13 +1745,28 @@ extern "C" int frx_model_evaluate(frx_model* m, frx_dataset* tr, frx_dataset* te
   CK(cudaMalloc(&d_topk, sizeof(int) * (size_t)std::max(1, nu) * max_k));
   CK(cudaMalloc(&d_rec, sizeof(float) * (size_t)std::max(1, nu) * nk));
   CK(cudaMalloc(&d_ndcg, sizeof(float) * (size_t)std::max(1, nu) * nk));
-  size_t chunk = ((size_t)512 << 20) / (sizeof(float) * (size_t)m->num_items);
-  chunk = std::max<size_t>(1, std::min<size_t>(chunk, (size_t)std::max(1, nu)));
-  CK(cudaMalloc(&d_scores, sizeof(float) * chunk * m->num_items));
-  p.k_list = d_k; p.nk = nk; p.max_k = max_k; p.scores = d_scores; p.chunk_users = (int)chunk;
+  p.k_list = d_k; p.nk = nk; p.max_k = max_k;
   p.topk = d_topk; p.recall = d_rec; p.ndcg = d_ndcg;
+  static const bool no_fused = getenv("FRX_DISABLE_TC") != nullptr || getenv("FRX_DISABLE_FUSED_EVAL") != nullptr;
+  void* d_ws = nullptr;
   c->stage_begin("evaluate");
-  launch_evaluate(p, c->stream, c->num_sms, &c->launches);
+  if (!no_fused && nu > 0 && score_topk_supported(d, max_k)) {
+    // fused tcgen05 scoring + top-k: no score matrix (recommender.h:109-112, 132-153)
+    CK(cudaMalloc(&d_ws, score_topk_workspace_bytes(nu, m->num_items, d, c->num_sms)));
+    const unsigned long long* lists = nullptr;
+    int segments = 0;
+    if (launch_score_topk(p, d_ws, c->num_sms, c->stream, &c->launches, &lists, &segments) != 0)
+      return fail(FRX_ERR_CUDA, "cuTensorMapEncodeTiled failed for the scoring operands");
+    CK(cudaGetLastError());
+    launch_merge_metrics(p, lists, segments, c->stream, &c->launches);
+  } else {
+    // any dimension / max_k > 128: tiled scores into a chunk buffer, then per-user radix select
+    size_t chunk = ((size_t)512 << 20) / (sizeof(float) * (size_t)m->num_items);
+    chunk = std::max<size_t>(1, std::min<size_t>(chunk, (size_t)std::max(1, nu)));
+    CK(cudaMalloc(&d_scores, sizeof(float) * chunk * m->num_items));
+    p.scores = d_scores; p.chunk_users = (int)chunk;
+    launch_evaluate(p, c->stream, c->num_sms, &c->launches);
+  }
   c->stage_end();
   CK(cudaGetLastError());
   if (nu) {
@@ -1681,7 +1777,7 @@ extern "C" int frx_model_evaluate(frx_model* m, frx_dataset* tr, frx_dataset* te
     if (user_ids) std::copy(tr->h_user_ids.begin(), tr->h_user_ids.end(), user_ids);
   }
   int rc = frx_context_sync(c);
-  cudaFree(Ut); cudaFree(d_k); cudaFree(d_topk); cudaFree(d_rec); cudaFree(d_ndcg); cudaFree(d_scores);
+  cudaFree(Ut); cudaFree(d_k); cudaFree(d_topk); cudaFree(d_rec); cudaFree(d_ndcg); cudaFree(d_scores); cudaFree(d_ws);
   if (rc) return rc;
   return nu;
 }

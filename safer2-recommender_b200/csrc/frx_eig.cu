@@ -108,7 +108,8 @@ __global__ void __cluster_dims__(TRI_CLUSTER, 1, 1) __launch_bounds__(TRI_THREAD
       if (j > k && tau != 0.0) {
         const double* col = Acol + lc * D;
 #pragma unroll
-        for (int e = 0; e < E; ++e) s = fma(col[lane + 32 * e], vloc[lane + 32 * e], s);
+        for (int e = 0; e < E; ++e)
+          if (32 * e + 31 > k) s = fma(col[lane + 32 * e], vloc[lane + 32 * e], s);  // v is zero up to k
         s = warp_sum_d(s) * tau;
       }
       if (lane == 0) ploc[lc] = s;
@@ -141,17 +142,19 @@ __global__ void __cluster_dims__(TRI_CLUSTER, 1, 1) __launch_bounds__(TRI_THREAD
 #pragma unroll
           for (int e = 0; e < E; ++e) {
             const int i = lane + 32 * e;
-            col[i] = fma(-vloc[i], wj, fma(-wloc[i], vj, col[i]));
+            if (32 * e + 31 > k) col[i] = fma(-vloc[i], wj, fma(-wloc[i], vj, col[i]));  // v, w are zero up to k
           }
         }
         {  // H[r, :] -= tau (H[r, :] . v) v^T
           double* row = Hrow + lc * D;
           double t = 0.0;
 #pragma unroll
-          for (int e = 0; e < E; ++e) t = fma(row[lane + 32 * e], vloc[lane + 32 * e], t);
+          for (int e = 0; e < E; ++e)
+            if (32 * e + 31 > k) t = fma(row[lane + 32 * e], vloc[lane + 32 * e], t);
           t = warp_sum_d(t) * tau;
 #pragma unroll
-          for (int e = 0; e < E; ++e) row[lane + 32 * e] = fma(-t, vloc[lane + 32 * e], row[lane + 32 * e]);
+          for (int e = 0; e < E; ++e)
+            if (32 * e + 31 > k) row[lane + 32 * e] = fma(-t, vloc[lane + 32 * e], row[lane + 32 * e]);
         }
       }
     }

@@ -16,6 +16,7 @@ namespace {
 
 constexpr int ST = 64;  // score tile edge
 constexpr int SK = 32;  // k chunk
+constexpr int CAND = FRX_TOPK_CAND;
 
 __global__ void __launch_bounds__(256) scores_kernel(const float* __restrict__ Ut, int nu_chunk,
                                                      const float* __restrict__ V, int num_items, int d,
@@ -64,7 +65,66 @@ __device__ __forceinline__ unsigned f2key(float f) {
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-constexpr int CAND = 1024;
+
+// Shared tail of the two top-k front ends: cand[0..CAND) holds 64-bit keys (score key << 32 | ~item), zeros for
+// empty slots.  Bitonic sort (descending), then hits against the ground truth and Recall@k / NDCG@k
+// (recommender.h:156-181).  The ground-truth size is the number of DISTINCT items of the user in test_te, like
+// the reference's std::set (recommender.h:183-188).
+__device__ void sort_and_score(const EvalParams& p, int row, int uid, int K, unsigned long long* cand,
+                               unsigned char* hit, unsigned* s_distinct) {
+  for (int size = 2; size <= CAND; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < CAND / 2; i += blockDim.x) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const unsigned long long a = cand[lo], b = cand[hi];
+        if ((a < b) == desc) { cand[lo] = b; cand[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  // ground truth
+  const int gb = (uid < p.te_rows) ? p.te_ptr[uid] : 0;
+  const int gcount = (uid < p.te_rows) ? p.te_ptr[uid + 1] - gb : 0;
+  if (threadIdx.x == 0) *s_distinct = 0;
+  __syncthreads();
+  {
+    unsigned mine = 0;
+    for (int g = threadIdx.x; g < gcount; g += blockDim.x) {
+      const int it = p.te_col[gb + g];
+      bool first = true;
+      for (int h = 0; h < g && first; ++h) first = (p.te_col[gb + h] != it);
+      mine += first ? 1u : 0u;
+    }
+    if (mine) atomicAdd(s_distinct, mine);
+  }
+  for (int r = threadIdx.x; r < K; r += blockDim.x) {
+    const int item = (int)(0xffffffffu - (unsigned)(cand[r] & 0xffffffffull));
+    if (p.topk) p.topk[(size_t)row * p.max_k + r] = item;
+    unsigned char h = 0;
+    for (int g = 0; g < gcount; ++g) h |= (p.te_col[gb + g] == item);
+    hit[r] = h;
+  }
+  __syncthreads();
+  const int gn = (int)*s_distinct;
+  if (threadIdx.x < p.nk) {
+    const int k = p.k_list[threadIdx.x];
+    float rec = 0.f, nd = 0.f;
+    if (gn > 0) {
+      double result = 0.0, dcg = 0.0;
+      for (int i = 0; i < k && i < K; ++i)
+        if (hit[i]) { result += 1.0; dcg += 1.0 / log2(i + 2.0); }
+      // recall: result / std::min<float>(k, gt_set.size())   (recommender.h:156-165)
+      rec = (float)(result / (double)fminf((float)k, (float)gn));
+      double norm = 0.0;
+      for (int i = 0; i < min(k, gn); ++i) norm += 1.0 / log2(i + 2.0);
+      nd = (float)(dcg / norm);  // recommender.h:168-181
+    }
+    p.recall[(size_t)row * p.nk + threadIdx.x] = rec;
+    p.ndcg[(size_t)row * p.nk + threadIdx.x] = nd;
+  }
+}
 
 // One CTA per held-out user: mask, top-max_k, metrics.
 __global__ void __launch_bounds__(256) topk_metrics_kernel(EvalParams p, int chunk_begin, int chunk_n) {
@@ -73,6 +133,7 @@ __global__ void __launch_bounds__(256) topk_metrics_kernel(EvalParams p, int chu
   __shared__ unsigned long long cand[CAND];
   __shared__ unsigned s_count;
   __shared__ unsigned char hit[CAND];
+  __shared__ unsigned s_distinct;
   const int cu = blockIdx.x;
   if (cu >= chunk_n) return;
   const int row = chunk_begin + cu;
@@ -131,46 +192,23 @@ __global__ void __launch_bounds__(256) topk_metrics_kernel(EvalParams p, int chu
     }
   }
   __syncthreads();
-  // bitonic sort, descending on (key, -index)
-  for (int size = 2; size <= CAND; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = threadIdx.x; i < CAND / 2; i += blockDim.x) {
-        const int lo = 2 * i - (i & (stride - 1));
-        const int hi = lo + stride;
-        const bool desc = ((lo & size) == 0);
-        const unsigned long long a = cand[lo], b = cand[hi];
-        if ((a < b) == desc) { cand[lo] = b; cand[hi] = a; }
-      }
-      __syncthreads();
-    }
-  }
-  // ground truth
-  const int gb = (uid < p.te_rows) ? p.te_ptr[uid] : 0;
-  const int gn = (uid < p.te_rows) ? p.te_ptr[uid + 1] - gb : 0;
-  for (int r = threadIdx.x; r < K; r += blockDim.x) {
-    const int item = (int)(0xffffffffu - (unsigned)(cand[r] & 0xffffffffull));
-    if (p.topk) p.topk[(size_t)row * p.max_k + r] = item;
-    unsigned char h = 0;
-    for (int g = 0; g < gn; ++g) h |= (p.te_col[gb + g] == item);
-    hit[r] = h;
-  }
+  sort_and_score(p, row, uid, K, cand, hit, &s_distinct);
+}
+
+// One CTA per held-out user: merge the per-segment candidate lists of the fused scoring kernel (frx_score_topk.cu).
+__global__ void __launch_bounds__(256) topk_merge_metrics_kernel(EvalParams p, const unsigned long long* __restrict__ lists,
+                                                                 int segments, int kpad) {
+  __shared__ unsigned long long cand[CAND];
+  __shared__ unsigned char hit[CAND];
+  __shared__ unsigned s_distinct;
+  const int row = blockIdx.x;
+  if (row >= p.nu) return;
+  const int uid = p.user_ids[row];
+  const int n = segments * kpad;
+  const unsigned long long* src = lists + (size_t)row * n;
+  for (int i = threadIdx.x; i < CAND; i += blockDim.x) cand[i] = i < n ? src[i] : 0ull;
   __syncthreads();
-  if (threadIdx.x < p.nk) {
-    const int k = p.k_list[threadIdx.x];
-    float rec = 0.f, nd = 0.f;
-    if (gn > 0) {
-      double result = 0.0, dcg = 0.0;
-      for (int i = 0; i < k && i < K; ++i)
-        if (hit[i]) { result += 1.0; dcg += 1.0 / log2(i + 2.0); }
-      // recall: result / std::min<float>(k, gt_set.size())   (recommender.h:156-165)
-      rec = (float)(result / (double)fminf((float)k, (float)gn));
-      double norm = 0.0;
-      for (int i = 0; i < min(k, gn); ++i) norm += 1.0 / log2(i + 2.0);
-      nd = (float)(dcg / norm);  // recommender.h:168-181
-    }
-    p.recall[(size_t)row * p.nk + threadIdx.x] = rec;
-    p.ndcg[(size_t)row * p.nk + threadIdx.x] = nd;
-  }
+  sort_and_score(p, row, uid, min(p.max_k, p.num_items), cand, hit, &s_distinct);
 }
 
 __global__ void row_ptr_kernel(const int* __restrict__ sorted_keys, int n, int nrows, int* __restrict__ ptr) {
@@ -192,6 +230,13 @@ __global__ void iota_kernel(int* p, int n) {
 }
 
 }  // namespace
+
+void launch_merge_metrics(const EvalParams& p, const unsigned long long* lists, int segments, cudaStream_t s,
+                          long long* launches) {
+  if (p.nu <= 0) return;
+  topk_merge_metrics_kernel<<<p.nu, 256, 0, s>>>(p, lists, segments, FRX_TOPK_PAD);
+  if (launches) ++*launches;
+}
 
 void launch_evaluate(const EvalParams& p, cudaStream_t s, int num_sms, long long* launches) {
   (void)num_sms;

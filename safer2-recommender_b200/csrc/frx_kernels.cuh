@@ -222,6 +222,18 @@ struct EvalParams {
 };
 void launch_evaluate(const EvalParams& p, cudaStream_t s, int num_sms, long long* launches);
 
+// Fused scoring + top-k (frx_score_topk.cu): tcgen05 Ut * V^T with the per-user top-max_k kept in the epilogue;
+// no score matrix.  d % 32 == 0 and max_k <= FRX_TOPK_PAD.  The candidate lists ([nu][segments][FRX_TOPK_PAD]
+// 64-bit keys) go to launch_merge_metrics, which sorts them and computes Recall / NDCG.
+constexpr int FRX_TOPK_PAD = 128;
+constexpr int FRX_TOPK_CAND = 1024;
+bool score_topk_supported(int d, int max_k);
+size_t score_topk_workspace_bytes(int nu, int num_items, int d, int num_sms);
+int launch_score_topk(const EvalParams& p, void* workspace, int num_sms, cudaStream_t s, long long* launches,
+                      const unsigned long long** cand_out, int* segments_out);
+void launch_merge_metrics(const EvalParams& p, const unsigned long long* lists, int segments, cudaStream_t s,
+                          long long* launches);
+
 // Dataset build: stable sort of tuple ids by row id -> ptr/col/tup (dataset.h:86-91).
 void build_csr(const int* d_keys, const int* d_other, int n, int nrows, int* ptr, int* col, int* tup,
                cudaStream_t s, long long* launches);

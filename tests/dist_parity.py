@@ -35,6 +35,7 @@ def main():
     failures = 0
     cases = [("safer2", 32, dict(uobs_weight=0.004, reg=0.004, bandwidth=0.15, use_snr=1, sampling_ratio=0.5, snr_seed=3)),
              ("safer2", 128, dict(uobs_weight=0.004, reg=0.004, bandwidth=0.15)),
+             ("safer2", 256, dict(uobs_weight=0.002, reg=0.002, bandwidth=0.18, use_snr=1, sampling_ratio=0.1, snr_seed=1)),
              ("ials", 32, dict(uobs_weight=0.1, reg=0.003)),
              ("erm_mf", 32, dict(uobs_weight=0.004, reg=0.005)),
              ("cvar_mf", 32, dict(uobs_weight=0.008, reg=0.002, stepsize=0.4))]

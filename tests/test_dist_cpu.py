@@ -87,10 +87,17 @@ def test_partition_rows_covers_and_balances():
     n = rng.integers(0, 200, 1000)
     ptr = np.concatenate([[0], np.cumsum(n)]).astype(np.int32)
     for world in (1, 2, 3, 8):
+        rb = pkg.partition_rows(ptr, world, row_unit=256)
+        assert rb[0] == 0 and rb[-1] == 1000 and np.all(np.diff(rb) >= 0)
+        cost = np.array([ptr[rb[k + 1]] - ptr[rb[k]] + 256 * np.count_nonzero(n[rb[k]:rb[k + 1]]) for k in range(world)])
+        assert cost.max() <= cost.sum() / world + 200 + 256
+        # built-in cost model (what frx_dataset_create uses): rows of at most 128 entries go to the dual-form
+        # kernel at a flat cost, longer rows to the direct kernel at length + 480
         rb = pkg.partition_rows(ptr, world)
         assert rb[0] == 0 and rb[-1] == 1000 and np.all(np.diff(rb) >= 0)
-        cost = np.array([ptr[rb[k + 1]] - ptr[rb[k]] + 256 * (rb[k + 1] - rb[k]) for k in range(world)])
-        assert cost.max() <= cost.sum() / world + 200 + 256
+        c = np.where(n == 0, 0, np.where(n <= 128, 150, n + 480))
+        cost = np.array([c[rb[k]:rb[k + 1]].sum() for k in range(world)])
+        assert cost.max() <= cost.sum() / world + c.max()
     # degenerate: fewer rows than ranks, empty matrix
     assert pkg.partition_rows(np.array([0, 5, 9], np.int32), 8)[-1] == 2
     assert list(pkg.partition_rows(np.array([0], np.int32), 4)) == [0, 0, 0, 0, 0]

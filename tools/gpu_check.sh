@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
-(timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 400 -s -k "bench_configuration or long_rows" 2>&1 | grep -v "^    \|^$" | tail -30) > gpurun_out/d_tests.log
-cat gpurun_out/d_tests.log
+(timeout 1000 python -m pytest tests -q -m gpu --timeout 400 2>&1 | tail -25) > gpurun_out/c_tests.log
+tail -12 gpurun_out/c_tests.log
 (timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --profile-stages > gpurun_out/c_bench.json) 2> gpurun_out/c_bench.err
 cat gpurun_out/c_bench.err | tail -14; python -c "
 import json; d=json.load(open('gpurun_out/c_bench.json')); print(d['ms_per_step'], d['e2e']['ms_per_step'], d['check'])"
