@@ -1624,57 +1624,42 @@ extern "C" int frx_model_compute_stats(frx_model* m, frx_dataset* ds, double* ou
   p.resid = ds->by_user.resid; p.chunk_row = ds->by_user.chunk_row; p.chunk_off = ds->by_user.chunk_off;
   p.num_chunks = ds->by_user.num_chunks;
   launch_user_loss(p, 0, nu, c->stream, c->num_sms, &c->launches);
-  std::vector<double> h_obs(nu);
-  std::vector<float> hU((size_t)nu * d), hV((size_t)ni * d), h_ireg(ni), h_loss(nu), GU((size_t)d * d), GV((size_t)d * d);
-  CK(cudaMemcpyAsync(h_obs.data(), obs, sizeof(double) * nu, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(hU.data(), m->U, sizeof(float) * hU.size(), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(hV.data(), m->V, sizeof(float) * hV.size(), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(h_ireg.data(), m->item_reg, sizeof(float) * ni, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(h_loss.data(), m->loss, sizeof(float) * nu, cudaMemcpyDeviceToHost, c->stream));
+  // everything is reduced on the device (one 8-double read-back): [0] observed, [1] reg, [2] user norms,
+  // [3] item norms, [4] sum(G_U o G_V), [5] sum of the per-user losses, [6], [7] scratch of the item pass
+  double* acc = nullptr;
+  CK(cudaMalloc(&acc, sizeof(double) * 8));
+  CK(cudaMemsetAsync(acc, 0, sizeof(double) * 8, c->stream));
+  launch_sum_d(obs, (size_t)nu, acc + 0, c->stream, c->num_sms, &c->launches);
+  const float uw = m->cfg.uobs_weight;
+  const bool ials = m->is_ials_family();
+  // users: reg_u = lambda (n_u + uw I)^nu (ials.h:310-315) or lambda (1 + uw I) (safer2.h:418-421)
+  launch_reg_sums(m->U, ds->by_user.ptr, ds->by_user.nrows, d, ials ? 0 : 1, m->cfg.reg, m->cfg.reg_exp, uw, m->cfg.alpha, ni,
+                  nullptr, acc + 6, c->stream, c->num_sms, &c->launches);
+  CK(cudaMemcpyAsync(acc + 2, acc + 7, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  CK(cudaMemcpyAsync(acc + 1, acc + 6, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  CK(cudaMemsetAsync(acc + 6, 0, sizeof(double) * 2, c->stream));
+  // items: reg_v = lambda (n_v + uw U)^nu or lambda (item_reg_v + alpha uw U) (safer2.h:426-432)
+  launch_reg_sums(m->V, ds->by_item.ptr, ds->by_item.nrows, d, ials ? 0 : 2, m->cfg.reg, m->cfg.reg_exp, uw, m->cfg.alpha, nu,
+                  m->item_reg, acc + 6, c->stream, c->num_sms, &c->launches);
+  CK(cudaMemcpyAsync(acc + 3, acc + 7, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   RC(gramian_into(m, m->U, nu, 0, d, 0, d, nullptr, m->Gz));
-  CK(cudaMemcpyAsync(GU.data(), m->Gz, sizeof(float) * GU.size(), cudaMemcpyDeviceToHost, c->stream));
   float* Gtmp = nullptr;
   CK(cudaMalloc(&Gtmp, sizeof(float) * (size_t)d * d));
   RC(gramian_into(m, m->V, ni, 0, d, 0, d, nullptr, Gtmp));
-  CK(cudaMemcpyAsync(GV.data(), Gtmp, sizeof(float) * GV.size(), cudaMemcpyDeviceToHost, c->stream));
+  launch_dot_sum(m->Gz, Gtmp, (size_t)d * d, acc + 4, c->stream, c->num_sms, &c->launches);
+  launch_dot_sum(m->loss, nullptr, (size_t)nu, acc + 5, c->stream, c->num_sms, &c->launches);
+  CK(cudaGetLastError());
+  double h[8];
+  CK(cudaMemcpyAsync(h, acc, sizeof h, cudaMemcpyDeviceToHost, c->stream));
   RC(frx_context_sync(c));
-  cudaFree(tmp_loss); cudaFree(obs); cudaFree(Gtmp);
-  const float uw = m->cfg.uobs_weight;
-  auto ials_reg = [&](int n, int choices) {
-    return (float)((double)m->cfg.reg * std::pow((double)((float)n + uw * (float)choices), (double)m->cfg.reg_exp));
-  };
-  double o = 0, reg = 0, ru = 0, ri = 0;
-  for (int u = 0; u < ds->by_user.nrows; ++u) {
-    const int n = ds->by_user.h_ptr[u + 1] - ds->by_user.h_ptr[u];
-    if (!n) continue;
-    o += h_obs[u];
-    double n2 = 0;
-    for (int k = 0; k < d; ++k) n2 += (double)hU[(size_t)u * d + k] * hU[(size_t)u * d + k];
-    reg += n2 * (m->is_ials_family() ? ials_reg(n, ni) : m->cfg.reg * (1 + uw * ni));
-    ru += n2;
-  }
-  for (int v = 0; v < ds->by_item.nrows; ++v) {
-    const int n = ds->by_item.h_ptr[v + 1] - ds->by_item.h_ptr[v];
-    if (!n) continue;
-    double n2 = 0;
-    for (int k = 0; k < d; ++k) n2 += (double)hV[(size_t)v * d + k] * hV[(size_t)v * d + k];
-    reg += n2 * (m->is_ials_family() ? ials_reg(n, nu) : m->cfg.reg * (h_ireg[v] + m->cfg.alpha * uw * nu));
-    ri += n2;
-  }
-  double unobs = 0;
-  for (size_t k = 0; k < GU.size(); ++k) unobs += (double)GU[k] * GV[k];
+  cudaFree(tmp_loss); cudaFree(obs); cudaFree(Gtmp); cudaFree(acc);
+  const double o = h[0], reg = h[1] + h[6], ru = h[2], ri = h[3], unobs = h[4];
   out6[1] = o / ds->num_tuples;
   out6[2] = unobs / ni / nu;
   out6[3] = reg;
   out6[4] = ru / nu;
   out6[5] = ri / ni;
-  if (m->is_ials_family()) {
-    out6[0] = o + uw * unobs + reg;
-  } else {
-    double l = 0;
-    for (float x : h_loss) l += x;
-    out6[0] = l;
-  }
+  out6[0] = ials ? o + uw * unobs + reg : h[5];
   return FRX_OK;
 }
 

@@ -201,6 +201,13 @@ void launch_norm_weights(const float* z, const float* hist_size, int n, float* o
                          long long* launches);
 
 void launch_fill(float* p, size_t n, float v, cudaStream_t s, long long* launches);
+// PrintLosses / ComputeLosses sums on the device (safer2.h:337-413, ials.h:226-305): out2[0] += sum_r |x_r|^2 * reg_r,
+// out2[1] += sum_r |x_r|^2 over the rows with history; kind 0 iALS, 1 SAFER2-family user, 2 SAFER2-family item.
+void launch_reg_sums(const float* X, const int* ptr, int rows, int d, int kind, float reg, float reg_exp, float uw,
+                     float alpha, int num_other, const float* item_reg, double* out2, cudaStream_t s, int num_sms,
+                     long long* launches);
+void launch_dot_sum(const float* a, const float* b, size_t n, double* out, cudaStream_t s, int num_sms, long long* launches);
+void launch_sum_d(const double* a, size_t n, double* out, cudaStream_t s, int num_sms, long long* launches);
 // *out += sum (a[i] - b[i])^2 (double); residual statistics (safer2.h:475-478, 550-553, 789-792)
 void launch_sqdiff(const float* a, const float* b, size_t n, double* out, cudaStream_t s, int num_sms, long long* launches);
 

@@ -54,8 +54,11 @@ struct WbRing {  // one published group
   float bscale[4];
 };
 
-struct WbSet {  // per solver set / accumulator slot
-  float buf[4][1024];   // per warp: transposed diagonal factor (when factoring) or its L panel block (when below)
+struct WbSet {  // per solver set / accumulator slot (a multiple of 1024 bytes: the tiles must be 1024-aligned)
+  // tf32 hi / lo operand tiles [128 rows][32] (K-major, SWIZZLE_128B) of the L panel for the tensor-core trailing
+  // update.  The 4 KB of rows 32w..32w+31 of the hi tile double as the transposed diagonal factor of warp w while
+  // the rows below run their triangular solve; after the factorisation the hi tile holds g, l, Dl^(-1/2), xt.
+  float tile[2][4096];
   int cidx[128];
   float sqs[128];       // sqrt(s_i)
   float tvec[128];      // rhs t_i
@@ -74,7 +77,7 @@ struct WbLayout {
   static constexpr int kRingOff = kSetOff + WB_NACC * (int)sizeof(WbSet);
   static constexpr int kSdOff = ((kRingOff + WB_RING * (int)sizeof(WbRing) + 15) / 16) * 16;
   static constexpr int kBarOff = ((kSdOff + WB_NLOADER * 64 * 4 + 15) / 16) * 16;
-  static constexpr int kNumBars = 2 * WB_NSTAGE + 3 * WB_NACC + 2 * WB_RING;
+  static constexpr int kNumBars = 2 * WB_NSTAGE + 4 * WB_NACC + 2 * WB_RING;
   static constexpr int kTotal = kBarOff + kNumBars * 8;
 };
 
@@ -99,12 +102,13 @@ __global__ void __launch_bounds__(WB_THREADS, 1) row_solve_wb_kernel(RowParams p
   uint64_t* gq_full = acc_empty + WB_NACC;             // [RING] scheduler
   uint64_t* gq_empty = gq_full + WB_RING;              // [RING] loaders + MMA warp + the 4 warps of the owning set
   uint64_t* acc_meta = gq_empty + WB_RING;             // [NACC] the per-slot arrays (cidx, sqs, tvec) are written
+  uint64_t* upd_bar = acc_meta + WB_NACC;              // [NACC] trailing update of the set's system complete
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     for (int i = 0; i < WB_NSTAGE; ++i) { mbar_init(&full_bar[i], 4); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < WB_NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); mbar_init(&acc_meta[i], 1); }
+    for (int i = 0; i < WB_NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); mbar_init(&acc_meta[i], 1); mbar_init(&upd_bar[i], 1); }
     for (int i = 0; i < WB_RING; ++i) { mbar_init(&gq_full[i], 1); mbar_init(&gq_empty[i], WB_NLOADER + 1 + 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -294,6 +298,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) row_solve_wb_kernel(RowParams p
     const int set = warp >> 2, w = warp & 3;
     WbSet& S = sets[set];
     const uint32_t tbase = tmem_base + ((uint32_t)(32 * w) << 16) + 128u * (uint32_t)set;  // block (w, j) at + 32 j
+    uint32_t upd_n = 0;  // trailing updates committed by this set so far
     for (uint32_t gseq = (uint32_t)set;; gseq += WB_NACC) {
       const uint32_t rsi = gseq % WB_RING;
       mbar_wait(&gq_full[rsi], (gseq / WB_RING) & 1);
@@ -319,20 +324,23 @@ __global__ void __launch_bounds__(WB_THREADS, 1) row_solve_wb_kernel(RowParams p
       float b_reg = used ? S.tvec[32 * w + lane] : 0.f;  // t_i, then y1_i, then y_i
       float a[32];
 
-      // ---- blocked right-looking Cholesky of (I + Fh Fh^T) restricted to my row's slots ----
+      // ---- blocked right-looking Cholesky of (I + Fh Fh^T) restricted to my row's slots: all rows of the group
+      //      advance panel by panel in lock step; diagonal blocks and triangular solves in registers (thread =
+      //      row), the trailing update C -= L21 L21^T of ALL rows of the group as ONE tensor-core product per
+      //      step (3xTF32, a_negate): warps that are not below a panel contribute zero rows ----
+      float* tile_hi = S.tile[0];
+      uint8_t* tile_hi_b = reinterpret_cast<uint8_t*>(S.tile[0]);
+      uint8_t* tile_lo_b = reinterpret_cast<uint8_t*>(S.tile[1]);
       for (int k = 0; k < nsteps; ++k) {
         const int pn = s0 + k;  // slot of the panel being eliminated in my row
+        const bool below = used && rel > k;
         if (used && rel == k) {
           // diagonal block: lane = row, column k scaled, published (transposed) and swept; rhs carried along
           uint32_t u[32];
           FRX_TMEM_LD32(u, tbase + 32u * (uint32_t)w);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(u[j]);
-          if (k == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j == lane) a[j] += 1.f;
-          }
-          float* LdT = S.buf[w];
+          for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(u[j]) + (j == lane ? 1.f : 0.f);  // + I
+          float* LdT = tile_hi + 1024 * w;
           float* rd = S.rd[w];
           float rs;
           bool bad_pivot;
@@ -373,13 +381,13 @@ __global__ void __launch_bounds__(WB_THREADS, 1) row_solve_wb_kernel(RowParams p
           S.y1[32 * w + lane] = b_reg;
         }
         set_barrier(set);  // A0: the diagonal factors of this step are published
-        if (used && rel > k) {
+        if (below) {
           // rows below: L21 row by forward substitution against the transposed L11 of slot pn
           uint32_t u[32];
           FRX_TMEM_LD32(u, tbase + 32u * (uint32_t)pn);
 #pragma unroll
           for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(u[j]);
-          const float* LdT = S.buf[pn];
+          const float* LdT = tile_hi + 1024 * pn;
           const float* rd = S.rd[pn];
 #pragma unroll
           for (int kk = 0; kk < 32; ++kk) {
@@ -394,7 +402,6 @@ __global__ void __launch_bounds__(WB_THREADS, 1) row_solve_wb_kernel(RowParams p
             }
           }
           float dot = 0.f;
-          float4* dst = reinterpret_cast<float4*>(S.buf[w] + lane * 32);
 #pragma unroll
           for (int k4 = 0; k4 < 8; ++k4) {
             const float4 y4 = reinterpret_cast<const float4*>(S.y1 + 32 * pn)[k4];
@@ -402,7 +409,6 @@ __global__ void __launch_bounds__(WB_THREADS, 1) row_solve_wb_kernel(RowParams p
             dot = fmaf(a[4 * k4 + 1], y4.y, dot);
             dot = fmaf(a[4 * k4 + 2], y4.z, dot);
             dot = fmaf(a[4 * k4 + 3], y4.w, dot);
-            dst[(k4 ^ (lane & 7)) & 7] = make_float4(a[4 * k4], a[4 * k4 + 1], a[4 * k4 + 2], a[4 * k4 + 3]);
           }
           b_reg -= dot;
 #pragma unroll
@@ -410,7 +416,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) row_solve_wb_kernel(RowParams p
           FRX_TMEM_ST32(tbase + 32u * (uint32_t)pn, u);  // the factor stays in TMEM for the back substitution
         } else if (used && rel == k) {
           // meanwhile the diagonal warp inverts its L11 (lane c = column c of the inverse) for the back substitution
-          const float* LdT = S.buf[w];
+          const float* LdT = tile_hi + 1024 * w;
           const float* rd = S.rd[w];
           float x[32];
 #pragma unroll
@@ -433,40 +439,45 @@ __global__ void __launch_bounds__(WB_THREADS, 1) row_solve_wb_kernel(RowParams p
           FRX_TMEM_ST32(tbase + 32u * (uint32_t)w, u);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        set_barrier(set);  // A: the L panel blocks of this step are published
-        if (used && rel > k) {
-          // trailing update of my block row: (w, j) -= L[w,pn] L[j,pn]^T for pn < j <= w
-          for (int j = pn + 1; j <= w; ++j) {
-            uint32_t u[32];
-            FRX_TMEM_LD32(u, tbase + 32u * (uint32_t)j);
-            const float4* Lj = reinterpret_cast<const float4*>(S.buf[j]);
-            float acc[32];
+        if (k + 1 < nsteps) {  // uniform over the set: some row of the group still has a trailing block
+          set_barrier(set);    // A1: the transposed factors have been read, their rows of the tile may be rewritten
+          {
+            const int mn = 32 * w + lane;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              float s0a = 0.f, s1a = 0.f;
+            for (int c4 = 0; c4 < 8; ++c4) {
+              float hi[4], lo[4];
 #pragma unroll
-              for (int k4 = 0; k4 < 8; k4 += 2) {
-                const float4 v0 = Lj[c * 8 + ((k4 ^ (c & 7)) & 7)];
-                const float4 v1 = Lj[c * 8 + (((k4 + 1) ^ (c & 7)) & 7)];
-                s0a = fmaf(a[4 * k4], v0.x, s0a);
-                s0a = fmaf(a[4 * k4 + 1], v0.y, s0a);
-                s0a = fmaf(a[4 * k4 + 2], v0.z, s0a);
-                s0a = fmaf(a[4 * k4 + 3], v0.w, s0a);
-                s1a = fmaf(a[4 * k4 + 4], v1.x, s1a);
-                s1a = fmaf(a[4 * k4 + 5], v1.y, s1a);
-                s1a = fmaf(a[4 * k4 + 6], v1.z, s1a);
-                s1a = fmaf(a[4 * k4 + 7], v1.w, s1a);
+              for (int t4 = 0; t4 < 4; ++t4) {
+                const float x = below ? a[4 * c4 + t4] : 0.f;
+                hi[t4] = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+                lo[t4] = x - hi[t4];
               }
-              acc[c] = __uint_as_float(u[c]) - (s0a + s1a);
-              if (k == 0 && j == w && c == lane) acc[c] += 1.f;  // first touch of my diagonal block: + I
+              const uint32_t off = tile_chunk_off(mn, c4);
+              *reinterpret_cast<float4*>(tile_hi_b + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<float4*>(tile_lo_b + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
             }
-#pragma unroll
-            for (int c = 0; c < 32; ++c) u[c] = __float_as_uint(acc[c]);
-            FRX_TMEM_ST32(tbase + 32u * (uint32_t)j, u);
           }
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          tc_fence_before();
+          set_barrier(set);    // A2: the L panel tile is complete, the factor blocks are in TMEM
+          if (w == 0 && lane == 0) {
+            tc_fence_after();
+            constexpr uint32_t idesc_neg = make_idesc_tf32(128, 1);
+            const uint32_t hi_addr = smem_u32(tile_hi_b), lo_addr = smem_u32(tile_lo_b);
+            const uint32_t d_tmem = tmem_base + 128u * (uint32_t)set;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t dhi = make_kmajor_desc(hi_addr + ks * 32), dlo = make_kmajor_desc(lo_addr + ks * 32);
+              umma_tf32(d_tmem, dhi, dhi, idesc_neg, 1u);
+              umma_tf32(d_tmem, dhi, dlo, idesc_neg, 1u);
+              umma_tf32(d_tmem, dlo, dhi, idesc_neg, 1u);
+            }
+            umma_commit(&upd_bar[set]);
+          }
+          mbar_wait(&upd_bar[set], upd_n & 1);
+          ++upd_n;
+          tc_fence_after();
         }
-        set_barrier(set);  // B: buffers may be overwritten by the next step
       }
 
       WB_LAP(1);
@@ -505,12 +516,12 @@ __global__ void __launch_bounds__(WB_THREADS, 1) row_solve_wb_kernel(RowParams p
       WB_LAP(2);
 
       // ---- g = sum_i coef_i Et[c_i]  (lane = feature; warp w takes features [w*D/4, (w+1)*D/4)) ----
-      // S.buf is free now: [0] g, [1] l, [2] Dl^(-1/2), [3] xt, each [4 row slots][D]
+      // the hi tile is free now: g, l, Dl^(-1/2), xt, each [4 row slots][D]
       constexpr int FW = D / 4, F = FW / 32;
-      float* gS = S.buf[0];
-      float* lS = S.buf[1];
-      float* rS = S.buf[2];
-      float* xS = S.buf[3];
+      float* gS = S.tile[0];
+      float* lS = S.tile[0] + 1024;
+      float* rS = S.tile[0] + 2048;
+      float* xS = S.tile[0] + 3072;
 #pragma unroll 1
       for (int s = 0; s < 4; ++s) {
         int desc = -1, n = 0;

@@ -658,6 +658,55 @@ __global__ void norm_weights_kernel(const float* __restrict__ z, const float* __
   const int u = blockIdx.x * blockDim.x + threadIdx.x;
   if (u < n) out[u] = z[u] / hs[u];
 }
+// PrintLosses / ComputeLosses regulariser sums (safer2.h:355-380, ials.h:246-262) on the device: one warp per row
+// with a non-empty history: out[0] += |x_r|^2 * reg_r, out[1] += |x_r|^2 (double; atomics: a printed statistic).
+// kind 0: iALS reg * (n + uw * num_other)^nu (ials.h:310-315); 1: SAFER2 user reg (1 + uw * num_other)
+// (safer2.h:418-421); 2: SAFER2 item reg (item_reg_v + alpha * uw * num_other) (safer2.h:426-432).
+__global__ void __launch_bounds__(256) reg_sums_kernel(const float* __restrict__ X, const int* __restrict__ ptr, int rows,
+                                                       int d, int kind, float reg, float reg_exp, float uw, float alpha,
+                                                       int num_other, const float* __restrict__ item_reg,
+                                                       double* __restrict__ out) {
+  __shared__ double sh[33];
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  double a = 0.0, b = 0.0;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+    const int n = ptr[r + 1] - ptr[r];
+    if (n == 0) continue;
+    double n2 = 0.0;
+    for (int k = lane; k < d; k += 32) {
+      const double v = (double)X[(size_t)r * d + k];
+      n2 += v * v;
+    }
+    n2 = warp_sum_d(n2);
+    float rf;
+    if (kind == 0) rf = (float)((double)reg * pow((double)((float)n + uw * (float)num_other), (double)reg_exp));
+    else if (kind == 1) rf = reg * (1 + uw * num_other);
+    else rf = reg * (item_reg[r] + alpha * uw * num_other);
+    if (lane == 0) { a += n2 * (double)rf; b += n2; }
+  }
+  a = block_sum_d(a, sh);
+  b = block_sum_d(b, sh);
+  if (threadIdx.x == 0) { atomicAdd(out, a); atomicAdd(out + 1, b); }
+}
+// *out += sum a[i] * b[i] (b may be null: sum a[i]); double
+__global__ void __launch_bounds__(256) dot_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n,
+                                                      double* __restrict__ out) {
+  __shared__ double sh[33];
+  double s = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    s += b ? (double)a[i] * (double)b[i] : (double)a[i];
+  s = block_sum_d(s, sh);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+__global__ void __launch_bounds__(256) sum_d_kernel(const double* __restrict__ a, size_t n, double* __restrict__ out) {
+  __shared__ double sh[33];
+  double s = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) s += a[i];
+  s = block_sum_d(s, sh);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
 // sum (a - b)^2 in double -> *out (atomic: a diagnostic, the order of the partial sums is not fixed)
 __global__ void __launch_bounds__(256) sqdiff_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n,
                                                      double* __restrict__ out) {
@@ -799,6 +848,30 @@ void launch_hist_and_item_reg(const int* uptr, int num_users_ds, float* hist_siz
 void launch_norm_weights(const float* z, const float* hist_size, int n, float* out, cudaStream_t s,
                          long long* launches) {
   norm_weights_kernel<<<(n + 255) / 256, 256, 0, s>>>(z, hist_size, n, out);
+  if (launches) ++*launches;
+}
+
+void launch_reg_sums(const float* X, const int* ptr, int rows, int d, int kind, float reg, float reg_exp, float uw,
+                     float alpha, int num_other, const float* item_reg, double* out2, cudaStream_t s, int num_sms,
+                     long long* launches) {
+  if (rows <= 0) return;
+  int g = (rows + 7) / 8;
+  if (g > num_sms * 8) g = num_sms * 8;
+  reg_sums_kernel<<<g, 256, 0, s>>>(X, ptr, rows, d, kind, reg, reg_exp, uw, alpha, num_other, item_reg, out2);
+  if (launches) ++*launches;
+}
+void launch_dot_sum(const float* a, const float* b, size_t n, double* out, cudaStream_t s, int num_sms, long long* launches) {
+  if (n == 0) return;
+  size_t g = (n + 255) / 256;
+  if (g > (size_t)num_sms * 8) g = (size_t)num_sms * 8;
+  dot_sum_kernel<<<(unsigned)g, 256, 0, s>>>(a, b, n, out);
+  if (launches) ++*launches;
+}
+void launch_sum_d(const double* a, size_t n, double* out, cudaStream_t s, int num_sms, long long* launches) {
+  if (n == 0) return;
+  size_t g = (n + 255) / 256;
+  if (g > (size_t)num_sms * 8) g = (size_t)num_sms * 8;
+  sum_d_kernel<<<(unsigned)g, 256, 0, s>>>(a, n, out);
   if (launches) ++*launches;
 }
 
