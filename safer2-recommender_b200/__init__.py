@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfrecsys_b200.so")
+# FRECSYS_B200_LIB: diagnostic override (experimental builds of the same library)
+LIB_PATH = os.environ.get("FRECSYS_B200_LIB") or os.path.join(HERE, "libfrecsys_b200.so")
 
 MODEL_IDS = {"ials": 0, "ialspp": 1, "erm_mf": 2, "cvar_mf": 3, "safer2": 4, "safer2pp": 5}
 

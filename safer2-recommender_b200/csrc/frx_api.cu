@@ -255,7 +255,7 @@ extern "C" int frx_context_create(int device, void* cuda_stream, frx_context** o
   CK(cudaMalloc(&c->dws, sizeof(double) * (xi_partials_doubles(c->num_sms) + 512)));
   CK(cudaMalloc(&c->status_dev, sizeof(int)));
   CK(cudaMemsetAsync(c->status_dev, 0, sizeof(int), c->stream));
-  CK(cudaMalloc(&c->wb_counter, 4 * sizeof(int)));
+  CK(cudaMalloc(&c->wb_counter, 8 * sizeof(int)));  // [4], [5]: launch_absmax
   *out = c;
   return FRX_OK;
 }
@@ -885,6 +885,10 @@ static int run_rows(frx_model* m, const RowCall& rc_) {
       p.dbg = dbg;
     }
     static const bool no_split = getenv("FRX_NO_SPLIT") != nullptr;
+    // bound of the SYRK operands (fp16 hi/lo pairs scaled by a power of two): max |E|, max entry weight
+    launch_absmax(p.E, (size_t)p.num_other * p.d, p.entry_w, (size_t)p.num_other,
+                  reinterpret_cast<unsigned*>(c->wb_counter + 4), c->stream, c->num_sms, &c->launches);
+    p.syrk_absmax = reinterpret_cast<const unsigned*>(c->wb_counter + 4);
     // rows with at most FRX_WB_MAX entries go to the dual-form kernel when the eigenbasis of G is at hand
     const bool use_wb = rc_.basis && rc_.basis->valid && rc_.rows->wb_num_groups > 0 && row_solve_wb_supported(p);
     const int direct_rows = use_wb ? rc_.rows->num_direct : rc_.rows->num_order;

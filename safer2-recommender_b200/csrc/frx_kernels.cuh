@@ -54,6 +54,9 @@ struct RowParams {
   float cg_tol;
   int cg_max_it;
   int* work_counter;  // tensor-core row kernel: work queue of the launch (zeroed by the launcher)
+  // tensor-core row kernel: bit patterns of max|E| and max entry weight (launch_absmax); the SYRK operands are
+  // fp16 hi + lo pairs of the entries scaled by a power of two derived from this bound
+  const unsigned* syrk_absmax;
   unsigned long long* dbg;  // optional per-phase cycle counters (FRX_TC_DEBUG), else null
   // Long rows (tensor-core path): a row with more than FRX_SPLIT_MIN entries is cut into pieces of
   // FRX_PIECE entries whose partial SYRK sums are produced by a first launch (piece_mode = 1, one
@@ -79,6 +82,9 @@ int row_solve_generic_grid(int num_rows, int num_sms);
 
 // tcgen05 / TMEM path (frx_row_tc.cu): full-dimension solves with d = 128 or 256.
 bool row_solve_tc_supported(const RowParams& p);
+// out[0] = bits(max |E[i]|), out[1] = bits(max |w[i]|) (0 without w); non-negative floats order like uints
+void launch_absmax(const float* E, size_t n, const float* w, size_t nw, unsigned* out, cudaStream_t s, int num_sms,
+                   long long* launches);
 void launch_row_solve_tc(const RowParams& p, cudaStream_t s, int num_sms, long long* launches);
 
 // Dual-form row path (frx_row_wb.cu) for rows with at most FRX_WB_MAX entries: needs the tridiagonal form

@@ -35,6 +35,7 @@
 #include "frx_kernels.cuh"
 #include "frx_tc_common.cuh"
 #include <cstdint>
+#include <cuda_fp16.h>
 
 namespace frx {
 
@@ -45,7 +46,8 @@ namespace {
 constexpr int TC_LOADER_WARPS = 16;               // 2 groups of 8
 constexpr int TC_THREADS = TC_LOADER_WARPS * 32;  // 4 warps per scheduler -> 128 registers per thread
 constexpr int TC_MMA_WARP = 15;                   // owns TMEM and issues the trailing updates
-constexpr int KT = 32;                                  // entries per operand tile (128 B rows) = panel width
+constexpr int KT = 32;                                  // panel width = entries per loader unit (lane = entry)
+constexpr int KS = 64;                                  // entries per SYRK operand tile: 128 B rows of fp16
 
 template <int D>
 struct TcLayout {
@@ -57,7 +59,12 @@ struct TcLayout {
   static constexpr int kLstFloats = 32 * (P * D - 16 * P * (P - 1));  // sum_p 32*(D-32p)
   static constexpr int kLstOff = kStageBytes;
   static constexpr int kPhaseB = kLstOff + kLstFloats * 4;
-  static constexpr int kBigBytes = kStagingBytes > kPhaseB ? kStagingBytes : kPhaseB;
+  // phase A: per loader warp one gather buffer (32 lanes x D/8 floats) that cp.async fills one unit ahead; it
+  // lies behind the operand stages and is aliased by the L panels of phase B
+  static constexpr int kGatherOff = kStagingBytes;
+  static constexpr int kGatherWarpBytes = 32 * (D / 8) * 4;
+  static constexpr int kPhaseA = kGatherOff + (TC_LOADER_WARPS - 1) * kGatherWarpBytes;
+  static constexpr int kBigBytes = kPhaseA > kPhaseB ? kPhaseA : kPhaseB;
   static constexpr int kRhsOff = kBigBytes;               // rhs partials [2][D]
   static constexpr int kLdOff = kRhsOff + 2 * D * 4;      // transposed diagonal factor, double-buffered [2][32][32]
   static constexpr int kWsumOff = kLdOff + 2 * 32 * 32 * 4;  // per-warp column sums [P][32]
@@ -184,8 +191,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
   const bool is_row_warp = warp < P;   // warp w owns matrix rows 32w .. 32w+31
 
   if (tid == 0) {
-    mbar_init(&full_bar[0], 8);
-    mbar_init(&full_bar[1], 8);
+    mbar_init(&full_bar[0], 2 * 8);  // units of a 64-entry tile: 2 entry halves x 8 feature slabs
+    mbar_init(&full_bar[1], 2 * 8);
     mbar_init(&empty_bar[0], 1);
     mbar_init(&empty_bar[1], 1);
     mbar_init(acc_bar, 1);
@@ -208,6 +215,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
   const int rq = warp & 3, rb = (D == 256) ? ((warp >> 2) & 1) : 0;
   const uint32_t trow = tmem_base + ((uint32_t)(32 * rq) << 16) + (rb ? 256u : 0u);
 
+  // Power-of-two scale of the fp16 SYRK operands: |sqrt(s) e| <= max|E| * sqrt(2 max w) < 2^ex  ->  sc = 2^(14 - ex).
+  // The accumulators then hold sc^2 * S: the rest of the system and the rhs are multiplied by sc^2 as well,
+  // which leaves the solution unchanged (exact scaling).
+  float sc = 1.f, sc2 = 1.f;
+  {
+    const float max_e = __uint_as_float(__ldg(p.syrk_absmax));
+    const float max_w = __uint_as_float(__ldg(p.syrk_absmax + 1));
+    const float bound = (p.mode == RM_SAFER_V) ? max_e * sqrtf(2.f * max_w) : max_e;
+    if (bound > 0.f && bound < 3.0e38f) {
+      int ex;
+      (void)frexpf(bound, &ex);  // bound = m * 2^ex, 0.5 <= m < 1
+      ex = max(-96, min(96, 14 - ex));
+      sc = exp2f((float)ex);
+      sc2 = sc * sc;
+    }
+  }
+  auto scaled_row_scalars = [&](int r_, int n_) {
+    RowScalars q = row_scalars(p, r_, n_);
+    q.alpha *= sc2; q.beta *= sc2; q.bscale *= sc2;
+    return q;
+  };
   // alpha*G + beta*I of the first row; for the later rows the warps that are idle during the back
   // substitution of the previous row do it (TMEM is free again by then)
   float* gbuf = reinterpret_cast<float*>(sm + L::kGbufOff) + warp * 1024;
@@ -217,7 +245,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
       tmem_init_system<D>(nullptr, 0.f, 0.f, tmem_base, warp & 3, warp >> 2, 4, gbuf, lane);
     } else {
       const int r0 = p.order[blockIdx.x];
-      const RowScalars s0 = row_scalars(p, r0, p.ptr[r0 + 1] - p.ptr[r0]);
+      const RowScalars s0 = scaled_row_scalars(r0, p.ptr[r0 + 1] - p.ptr[r0]);
       if (LONG) {
         const int n0 = p.ptr[r0 + 1] - p.ptr[r0];
         tmem_init_system<D>(p.G, s0.alpha, s0.beta, tmem_base, warp & 3, warp >> 2, 4, gbuf, lane,
@@ -253,7 +281,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
     const int e0 = PIECE ? p.piece_off[ri] : 0;             // first entry gathered here
     const int pc_row = LONG ? p.row_piece0[r] : -1;         // first piece of a pre-summed long row
     const int n_here = PIECE ? min(FRX_PIECE, n - e0) : (LONG ? 0 : n);
-    const int T = (n_here + KT - 1) / KT;
+    const int T = (n_here + KS - 1) / KS;  // SYRK operand tiles
     int dup_lo = 0, dup_hi = 0;
     if (item_side && n > 128 && (n & 127) != 0) {  // stale tail, safer2.h:200-204 (B-1)
       const int kf = n >> 7;
@@ -271,27 +299,71 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
       // The 15 loader warps take the (tile, feature slab) units of the row round-robin; a stage is full
       // after eight unit arrivals.  (The MMA-issuing thread blocks for most of a tile's MMA time, so it
       // cannot double as a loader without delaying its group's next tile.)
-      const uint32_t kq = (uint32_t)(lane >> 2), kr = (uint32_t)(lane & 3) << 2;
-      for (int u = warp; u < SL * T; u += TC_LOADER_WARPS - 1) {
-        const int t = u / SL, w8 = u % SL;
+      // Software pipeline of the gather (measured: the SYRK phase was bound by the latency of the dependent chain
+      // col -> entry_w -> E row, not by the tensor pipe): the indices run two units ahead of the unit being
+      // converted, the weight and the E slab one unit ahead.  The slab travels by cp.async into this warp's gather
+      // buffer (lane l owns 4C bytes, its 16-byte chunks XOR-swizzled so that the LDS.128 read-back is
+      // conflict-free), so the data of unit k+1 is in flight while unit k is split and stored.
+      constexpr int STEP = TC_LOADER_WARPS - 1;
+      const uint32_t gbase = sm_addr + L::kGatherOff + (uint32_t)warp * L::kGatherWarpBytes + (uint32_t)lane * (C * 4);
+      const uint32_t gkey = F4 == 8 ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
+      const int n_units = 2 * SL * T;  // unit u: tile u / 16, entry half (u / 8) & 1, feature slab u % 8
+      auto entry_of = [&](int u) { return e0 + (u / SL) * KT + lane; };
+      auto unit_valid = [&](int u) { return u < n_units && entry_of(u) < e0 + n_here; };
+      auto issue_gather = [&](int u, int c, bool ok) {
+        const float* src = p.E + (size_t)c * D + (u % SL) * C;
+#pragma unroll
+        for (int j = 0; j < F4; ++j)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(gbase + ((((uint32_t)j ^ gkey) & (F4 - 1)) << 4)),
+                       "l"(src + 4 * j), "r"(ok ? 16 : 0)
+                       : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      int c_1 = 0;        // index of the entry of unit u + STEP
+      float w_cur = 1.f;  // weight of the entry of unit u
+      if (warp < n_units) {
+        int c_0 = 0;
+        const bool ok0 = unit_valid(warp);
+        if (ok0) c_0 = __ldg(p.col + beg + entry_of(warp));
+        if (unit_valid(warp + STEP)) c_1 = __ldg(p.col + beg + entry_of(warp + STEP));
+        if (ok0 && item_side) w_cur = __ldg(p.entry_w + c_0);
+        issue_gather(warp, ok0 ? c_0 : 0, ok0);
+      }
+      for (int u = warp; u < n_units; u += STEP) {
+        const int t = u / (2 * SL), w8 = u % SL;
+        const int half = (u / SL) & 1;  // which 32 entries of the 64-entry tile
         const int slab = w8 * C;  // first feature of this unit
-        const int e = e0 + t * KT + lane;  // entry index within the row
+        const int e = entry_of(u);  // entry index within the row
         const bool valid = e < e0 + n_here;
+        const float wgt = w_cur;
         float4 v[F4];
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < F4; ++j) {
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(v[j].x), "=f"(v[j].y), "=f"(v[j].z), "=f"(v[j].w)
+                       : "r"(gbase + ((((uint32_t)j ^ gkey) & (F4 - 1)) << 4))
+                       : "memory");
+#ifdef FRX_EXP_NOLOAD
+          v[j] = make_float4(0.01f * e, 0.02f, 0.03f, 0.04f);
+#endif
+        }
+        {  // next unit's slab and weight, the index of the one after
+          const int u1 = u + STEP, u2 = u + 2 * STEP;
+          const bool ok1 = unit_valid(u1);
+          if (u1 < n_units) {
+            issue_gather(u1, ok1 ? c_1 : 0, ok1);
+            w_cur = (ok1 && item_side) ? __ldg(p.entry_w + c_1) : 1.f;
+          }
+          if (unit_valid(u2)) c_1 = __ldg(p.col + beg + entry_of(u2));
+        }
         float sq = 0.f, qr = 0.f;
         if (valid) {
-          const int c = __ldg(p.col + beg + e);
           float s = 1.f, q = 1.f;
-          if (item_side) { const float w = __ldg(p.entry_w + c); s = w; q = w; }
+          if (item_side) { s = wgt; q = wgt; }
           if (e >= dup_lo && e < dup_hi) s *= 2.f;
           sq = sqrtf(s);
           qr = s > 0.f ? q / sq : 0.f;
-          const float4* src = reinterpret_cast<const float4*>(p.E + (size_t)c * D + slab);
-#pragma unroll
-          for (int j = 0; j < F4; ++j) v[j] = __ldg(src + j);
-        } else {
-#pragma unroll
-          for (int j = 0; j < F4; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         const uint32_t gt = row_tile0 + (uint32_t)t;
         const int st = (int)(gt & 1u);
@@ -299,20 +371,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
         if (use > 0) mbar_wait(&empty_bar[st], (use - 1) & 1);  // stage free again
         uint8_t* hi_tile = sm + st * L::kStageBytes;
         uint8_t* lo_tile = hi_tile + L::kTileBytes;
+        // x = sqrt(s) e (fp32, as before); the operands are fp16 pairs hi = rn(x * sc), lo = rn(x * sc - hi)
+        // (fp16 has the 11 significand bits of tf32, so hi*hi + hi*lo + lo*hi is at least as accurate as 3xTF32
+        // while an MMA covers K = 16 instead of 8 and the operand tiles are half as large).  Adjacent lanes swap
+        // half of their features so that every lane stores entry PAIRS as 32-bit words: even lanes keep the
+        // features with (f & 4) == 0, odd lanes the others -> conflict-free under the 128B swizzle.
         float rv[C];
 #pragma unroll
         for (int j = 0; j < F4; ++j) {
-          const float x4[4] = {v[j].x * sq, v[j].y * sq, v[j].z * sq, v[j].w * sq};
+          v[j].x *= sq; v[j].y *= sq; v[j].z *= sq; v[j].w *= sq;
+          rv[4 * j + 0] = qr * v[j].x; rv[4 * j + 1] = qr * v[j].y; rv[4 * j + 2] = qr * v[j].z; rv[4 * j + 3] = qr * v[j].w;
+        }
+        const bool odd = (lane & 1) != 0;
+        const uint32_t wd = 16u * (uint32_t)half + (uint32_t)(lane >> 1);  // 32-bit word (entry pair) within the 128 B row
+        const uint32_t wchunk = wd >> 2, wbyte = (wd & 3u) << 2;
+#pragma unroll
+        for (int m = 0; m < F4 / 2; ++m) {
+          const float4 keep = odd ? v[2 * m + 1] : v[2 * m];
+          const float4 send = odd ? v[2 * m] : v[2 * m + 1];
+          float4 recv;
+          recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+          recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+          recv.z = __shfl_xor_sync(0xffffffffu, send.z, 1);
+          recv.w = __shfl_xor_sync(0xffffffffu, send.w, 1);
+          const float4 ev = odd ? recv : keep;  // entry 2j   (lower address)
+          const float4 od = odd ? keep : recv;  // entry 2j+1
+          const float e0v[4] = {ev.x * sc, ev.y * sc, ev.z * sc, ev.w * sc};
+          const float e1v[4] = {od.x * sc, od.y * sc, od.z * sc, od.w * sc};
 #pragma unroll
           for (int t4 = 0; t4 < 4; ++t4) {
-            const int mn = slab + 4 * j + t4;
-            const float x = x4[t4];
-            const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-            const float lo = x - hi;
-            const uint32_t off = tile_chunk_off(mn, (int)kq) + kr;
-            *reinterpret_cast<float*>(hi_tile + off) = hi;
-            *reinterpret_cast<float*>(lo_tile + off) = lo;
-            rv[4 * j + t4] = qr * x;
+            const int mn = slab + 8 * m + (odd ? 4 : 0) + t4;
+            const __half2 hh = __floats2half2_rn(e0v[t4], e1v[t4]);
+            const float2 hf = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn(e0v[t4] - hf.x, e1v[t4] - hf.y);
+            const uint32_t off = tile_chunk_off(mn, (int)wchunk) + wbyte;
+#ifdef FRX_EXP_NOSTORE
+            if (hf.x == 123.f) { *reinterpret_cast<__half2*>(hi_tile + off) = hh; *reinterpret_cast<__half2*>(lo_tile + off) = ll; }
+#else
+            *reinterpret_cast<__half2*>(hi_tile + off) = hh;
+            *reinterpret_cast<__half2*>(lo_tile + off) = ll;
+#endif
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -324,8 +422,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
       }
     } else {
       // ================= MMA issuer: SYRK, tiles in order =================
-      constexpr uint32_t idesc_n128 = make_idesc_tf32(128);
-      constexpr uint32_t idesc_n256 = make_idesc_tf32(256);
+      constexpr uint32_t idesc_n128 = make_idesc_f16(128);
+      constexpr uint32_t idesc_n256 = make_idesc_f16(256);
       for (int t = 0; t < T; ++t) {
         const uint32_t gt = row_tile0 + (uint32_t)t;
         const int st = (int)(gt & 1u);
@@ -334,22 +432,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
         if (lane == 0) {
           const uint32_t hi_addr = sm_addr + st * L::kStageBytes;
           const uint32_t lo_addr = hi_addr + L::kTileBytes;
-#pragma unroll
-          for (int ks = 0; ks < KT / 8; ++ks) {
+          const int ksteps = min(KS / 16, (n_here - t * KS + 15) >> 4);  // 16 entries per MMA; the tail is zero-filled
+#pragma unroll 1
+          for (int ks = 0; ks < ksteps; ++ks) {
             const uint32_t ko = ks * 32;
             const uint64_t b_hi = make_kmajor_desc(hi_addr + ko);
             const uint64_t b_lo = make_kmajor_desc(lo_addr + ko);
             {  // rows 0..127 x cols 0..127 -> TMEM columns [0,128); accumulates onto alpha*G + beta*I
-              umma_tf32(tmem_base, b_hi, b_hi, idesc_n128, 1u);
-              umma_tf32(tmem_base, b_hi, b_lo, idesc_n128, 1u);
-              umma_tf32(tmem_base, b_lo, b_hi, idesc_n128, 1u);
+              umma_f16(tmem_base, b_hi, b_hi, idesc_n128, 1u);
+#ifndef FRX_EXP_HIONLY
+              umma_f16(tmem_base, b_hi, b_lo, idesc_n128, 1u);
+              umma_f16(tmem_base, b_lo, b_hi, idesc_n128, 1u);
+#endif
             }
             if (D == 256) {  // rows 128..255 x cols 0..255 -> TMEM columns [256,512)
               const uint64_t a_hi = make_kmajor_desc(hi_addr + 128 * 128 + ko);
               const uint64_t a_lo = make_kmajor_desc(lo_addr + 128 * 128 + ko);
-              umma_tf32(tmem_base + 256, a_hi, b_hi, idesc_n256, 1u);
-              umma_tf32(tmem_base + 256, a_hi, b_lo, idesc_n256, 1u);
-              umma_tf32(tmem_base + 256, a_lo, b_hi, idesc_n256, 1u);
+              umma_f16(tmem_base + 256, a_hi, b_hi, idesc_n256, 1u);
+#ifndef FRX_EXP_HIONLY
+              umma_f16(tmem_base + 256, a_hi, b_lo, idesc_n256, 1u);
+              umma_f16(tmem_base + 256, a_lo, b_hi, idesc_n256, 1u);
+#endif
             }
           }
           umma_commit(&empty_bar[st]);
@@ -376,7 +479,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
     const int ri_next = next_item_s;  // stable until thread 0 writes it again at the top of the next item
     FRX_DBG_LAP(0);  // phase A (gather + SYRK)
 
-    const RowScalars rs_row = row_scalars(p, r, n);
+    const RowScalars rs_row = scaled_row_scalars(r, n);
     float b_reg = 0.f;  // this row-thread's rhs element, then y_i, then x_i
     if (is_row_warp) {
       const int i = 32 * warp + lane;
@@ -656,7 +759,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
       if (rin < p.num_rows) {
         const int rn = p.order[rin];
         const int nn = p.ptr[rn + 1] - p.ptr[rn];
-        const RowScalars sn = row_scalars(p, rn, nn);
+        const RowScalars sn = scaled_row_scalars(rn, nn);
         constexpr int nshare = (TC_LOADER_WARPS - P) / 4;
         tc_fence_after();
         if (LONG)

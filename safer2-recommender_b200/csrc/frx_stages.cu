@@ -707,6 +707,29 @@ __global__ void __launch_bounds__(256) sum_d_kernel(const double* __restrict__ a
   if (threadIdx.x == 0) atomicAdd(out, s);
 }
 
+// out[0] = max(out[0], bits(max |a[i]|)), out[1] likewise for w (non-negative floats compare like their bit patterns)
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ a, size_t n, const float* __restrict__ w,
+                                                     size_t nw, unsigned* __restrict__ out) {
+  float m = 0.f, mw = 0.f;
+  const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n4 = n / 4;
+  for (size_t i = i0; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(a) + i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  for (size_t i = 4 * n4 + i0; i < n; i += stride) m = fmaxf(m, fabsf(a[i]));
+  for (size_t i = i0; i < nw; i += stride) mw = fmaxf(mw, fabsf(w[i]));
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, off));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(out, __float_as_uint(m));
+    if (w) atomicMax(out + 1, __float_as_uint(mw));
+  }
+}
+
 // sum (a - b)^2 in double -> *out (atomic: a diagnostic, the order of the partial sums is not fixed)
 __global__ void __launch_bounds__(256) sqdiff_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n,
                                                      double* __restrict__ out) {
@@ -875,6 +898,15 @@ void launch_sum_d(const double* a, size_t n, double* out, cudaStream_t s, int nu
   if (launches) ++*launches;
 }
 
+void launch_absmax(const float* E, size_t n, const float* w, size_t nw, unsigned* out, cudaStream_t s, int num_sms,
+                   long long* launches) {
+  cudaMemsetAsync(out, 0, 2 * sizeof(unsigned), s);
+  size_t g = (n / 4 + 255) / 256;
+  if (g > (size_t)num_sms * 8) g = (size_t)num_sms * 8;
+  if (g == 0) g = 1;
+  absmax_kernel<<<(unsigned)g, 256, 0, s>>>(E, n, w, w ? nw : 0, out);
+  if (launches) ++*launches;
+}
 void launch_sqdiff(const float* a, const float* b, size_t n, double* out, cudaStream_t s, int num_sms, long long* launches) {
   if (n == 0) return;
   size_t g = (n + 255) / 256;

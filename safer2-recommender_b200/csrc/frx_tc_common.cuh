@@ -68,6 +68,13 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -108,6 +115,10 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int N, int a_negate = 0) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_negate & 1) << 13) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(128 >> 4) << 24);
+}
+// kind::f16 with fp16 A and B (format 0), fp32 accumulate, K-major, M = 128: K = 16 per instruction
+__host__ __device__ constexpr uint32_t make_idesc_f16(int N, int a_negate = 0) {
+  return (1u << 4) | ((uint32_t)(a_negate & 1) << 13) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 // byte offset of element (row mn, k-chunk c of 4 floats) in a K-major SWIZZLE_128B tile with 128 B rows
 __device__ __forceinline__ uint32_t tile_chunk_off(int mn, int c) {
