@@ -164,6 +164,7 @@ struct Csr {
   int* chunk_row = nullptr;
   int* chunk_off = nullptr;
   float* resid = nullptr;  // [nnz]
+  mutable float* ew = nullptr;  // [nnz] per-entry weights of the tensor-core item half-step (allocated on first use)
   // dual-form row path: the rows of `order` with at most FRX_WB_MAX entries (its tail: order is longest first)
   // packed into groups of four 32-entry slots (WbParams::grp_slots)
   int num_direct = 0;      // order[0, num_direct) have more than FRX_WB_MAX entries
@@ -509,7 +510,7 @@ extern "C" void frx_dataset_destroy(frx_dataset* d) {
   for (Csr* m : {&d->by_user, &d->by_item}) {
     cudaFree(m->ptr); cudaFree(m->col); cudaFree(m->tup); cudaFree(m->order);
     cudaFree(m->piece_row); cudaFree(m->piece_off); cudaFree(m->row_piece0);
-    cudaFree(m->chunk_row); cudaFree(m->chunk_off); cudaFree(m->resid);
+    cudaFree(m->chunk_row); cudaFree(m->chunk_off); cudaFree(m->resid); cudaFree(m->ew);
     cudaFree(m->wb_groups);
   }
   cudaFree(d->xmap);
@@ -889,6 +890,14 @@ static int run_rows(frx_model* m, const RowCall& rc_) {
     launch_absmax(p.E, (size_t)p.num_other * p.d, p.entry_w, (size_t)p.num_other,
                   reinterpret_cast<unsigned*>(c->wb_counter + 4), c->stream, c->num_sms, &c->launches);
     p.syrk_absmax = reinterpret_cast<const unsigned*>(c->wb_counter + 4);
+    if (p.entry_w && !rc_.rows->h_ptr.empty()) {
+      // the weight of every history entry of this rank's rows, aligned with col (staged with the indices)
+      const Csr* rw = rc_.rows;
+      if (!rw->ew) CK(cudaMalloc(&rw->ew, sizeof(float) * (size_t)std::max(1, rw->h_ptr[rw->nrows])));
+      const int rb = rc_.xmap ? 0 : rw->rank_begin[c->rank], re = rc_.xmap ? rw->nrows : rw->rank_begin[c->rank + 1];
+      launch_entry_weights(p.col, p.entry_w, (size_t)rw->h_ptr[rb], (size_t)rw->h_ptr[re], rw->ew, c->stream, &c->launches);
+      p.entry_w_e = rw->ew;
+    }
     // rows with at most FRX_WB_MAX entries go to the dual-form kernel when the eigenbasis of G is at hand
     const bool use_wb = rc_.basis && rc_.basis->valid && rc_.rows->wb_num_groups > 0 && row_solve_wb_supported(p);
     const int direct_rows = use_wb ? rc_.rows->num_direct : rc_.rows->num_order;

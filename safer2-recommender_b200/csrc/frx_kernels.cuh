@@ -38,6 +38,7 @@ struct RowParams {
   const int* xmap;     // row id -> row of X (fold-in evaluation), or null
   const float* G;      // [d x d] (weighted) Gramian of the fixed side
   const float* entry_w;   // per fixed-side-row weight w_c = z_c/n_c (item side) or null
+  const float* entry_w_e; // the same weights per history ENTRY (aligned with col: launch_entry_weights), or null
   const float* row_w;     // per-row dual weight z_u (user side) or null (= 1)
   const float* item_reg;  // item side: sum_{u in hist} 1/n_u
   float* pred;            // ++ prediction cache, indexed by tuple
@@ -72,7 +73,8 @@ struct RowParams {
 };
 // (The piece length also bounds the accumulation chain inside the tensor cores, whose fp32 accumulator rounds
 // toward zero: 128 MMA steps per TMEM pass keep that bias near 4e-6; the pieces are added with IEEE fp32 adds.)
-constexpr int FRX_SPLIT_MIN = 2048;
+constexpr int FRX_STAGE_CAP = 1792;  // history entries of a work item whose indices / weights the tensor-core row kernel stages
+constexpr int FRX_SPLIT_MIN = FRX_STAGE_CAP;
 constexpr int FRX_PIECE = 1024;
 size_t row_solve_tc_piece_floats(int d);  // piece_stride for dimension d
 
@@ -82,6 +84,9 @@ int row_solve_generic_grid(int num_rows, int num_sms);
 
 // tcgen05 / TMEM path (frx_row_tc.cu): full-dimension solves with d = 128 or 256.
 bool row_solve_tc_supported(const RowParams& p);
+// ew[e] = w[col[e]] for the entries e in [e_begin, e_end)
+void launch_entry_weights(const int* col, const float* w, size_t e_begin, size_t e_end, float* ew, cudaStream_t s,
+                          long long* launches);
 // out[0] = bits(max |E[i]|), out[1] = bits(max |w[i]|) (0 without w); non-negative floats order like uints
 void launch_absmax(const float* E, size_t n, const float* w, size_t nw, unsigned* out, cudaStream_t s, int num_sms,
                    long long* launches);

@@ -63,7 +63,9 @@ struct TcLayout {
   // lies behind the operand stages and is aliased by the L panels of phase B
   static constexpr int kGatherOff = kStagingBytes;
   static constexpr int kGatherWarpBytes = 32 * (D / 8) * 4;
-  static constexpr int kPhaseA = kGatherOff + (TC_LOADER_WARPS - 1) * kGatherWarpBytes;
+  // ... followed by the staged indices and weights of the work item's history entries (also phase A only)
+  static constexpr int kIdxOff = kGatherOff + (TC_LOADER_WARPS - 1) * kGatherWarpBytes;
+  static constexpr int kPhaseA = kIdxOff + 2 * FRX_STAGE_CAP * 4;
   static constexpr int kBigBytes = kPhaseA > kPhaseB ? kPhaseA : kPhaseB;
   static constexpr int kRhsOff = kBigBytes;               // rhs partials [2][D]
   static constexpr int kLdOff = kRhsOff + 2 * D * 4;      // transposed diagonal factor, double-buffered [2][32][32]
@@ -289,6 +291,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
       dup_hi = 128 * kf;
     }
 
+    // The indices (and item-side weights) of the work item's entries go to shared memory first: the gather loop
+    // below then contains no dependent global load at all (measured: with per-unit index / weight LDGs the loader
+    // warps sat on the long scoreboard for a third of their time).  Longer histories than the staging capacity
+    // (FRX_NO_SPLIT) read the tail from global memory.
+    int* colS = reinterpret_cast<int*>(sm + L::kIdxOff);
+    float* wS = reinterpret_cast<float*>(sm + L::kIdxOff + FRX_STAGE_CAP * 4);
+    {
+      const int ns = min(n_here, FRX_STAGE_CAP);
+      for (int i = tid; i < ns; i += TC_THREADS) {
+        const int c = __ldg(p.col + beg + e0 + i);
+        colS[i] = c;
+        if (item_side) wS[i] = p.entry_w_e ? __ldg(p.entry_w_e + beg + e0 + i) : __ldg(p.entry_w + c);
+      }
+    }
+    __syncthreads();
     const uint32_t row_tile0 = tile_base;  // CTA-wide index of this row's first tile: stage = index & 1
     constexpr int SL = D / C;              // 32-entry x C-feature units per tile (8)
     float rhs_acc[SL];
@@ -299,124 +316,172 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
       // The 15 loader warps take the (tile, feature slab) units of the row round-robin; a stage is full
       // after eight unit arrivals.  (The MMA-issuing thread blocks for most of a tile's MMA time, so it
       // cannot double as a loader without delaying its group's next tile.)
-      // Software pipeline of the gather (measured: the SYRK phase was bound by the latency of the dependent chain
-      // col -> entry_w -> E row, not by the tensor pipe): the indices run two units ahead of the unit being
-      // converted, the weight and the E slab one unit ahead.  The slab travels by cp.async into this warp's gather
-      // buffer (lane l owns 4C bytes, its 16-byte chunks XOR-swizzled so that the LDS.128 read-back is
-      // conflict-free), so the data of unit k+1 is in flight while unit k is split and stored.
+      // Software pipeline of the gather (measured: the SYRK phase was bound first by the latency of the dependent
+      // chain col -> entry_w -> E row, then by the instruction count of the conversion, never by the tensor pipe):
+      //  * indices and weights come from the staged arrays; the E slab of the NEXT unit travels by cp.async into
+      //    this warp's gather buffer (lane = history entry, 4C bytes per lane, 16-byte chunks XOR-swizzled) while
+      //    the current unit is converted;
+      //  * the buffer is read back with lane (2j + o) taking the ENTRY PAIR (2j, 2j+1) and the float4 columns
+      //    of parity o: exactly the distribution the fp16 operand tiles want (a 32-bit word = two adjacent
+      //    entries of one feature; even lanes touch feature rows with (f & 4) == 0, odd lanes the others, which
+      //    is conflict-free under the 128B swizzle) -- no register exchange at all;
+      //  * operands: x = sqrt(s) e scaled by sc, hi = rn_fp16(x), lo = rn_fp16(x - hi) (fp16 carries the 11
+      //    significand bits of tf32: hi*hi + hi*lo + lo*hi is at least as accurate as 3xTF32, an MMA covers
+      //    K = 16 instead of 8 and the tiles are half as large);
+      //  * rhs: q_2j e_2j + q_2j+1 e_2j+1 per lane, then a 15-shuffle transpose-reduce over the 16 lanes of
+      //    equal parity leaves one feature of the slab in every lane.
       constexpr int STEP = TC_LOADER_WARPS - 1;
-      const uint32_t gbase = sm_addr + L::kGatherOff + (uint32_t)warp * L::kGatherWarpBytes + (uint32_t)lane * (C * 4);
-      const uint32_t gkey = F4 == 8 ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
+      constexpr int H4 = F4 / 2;  // float4 columns per lane after the read-back
+      const uint32_t gwarp = sm_addr + L::kGatherOff + (uint32_t)warp * L::kGatherWarpBytes;
+      const int o = lane & 1, pj = lane >> 1;
+      // read-back addresses of my pair: entry i -> row i, chunk (2m + o) ^ key(i); at D = 128 (64 B rows) the odd
+      // lanes read the odd entry first so that a quarter-warp still covers all 32 banks
+      const int i0 = 2 * pj, i1 = 2 * pj + 1;
+      const uint32_t key0 = F4 == 8 ? (uint32_t)(i0 & 7) : (uint32_t)(pj & 3);
+      const uint32_t key1 = F4 == 8 ? (uint32_t)(i1 & 7) : (uint32_t)(pj & 3);
+      const uint32_t grow0 = gwarp + (uint32_t)i0 * (C * 4), grow1 = gwarp + (uint32_t)i1 * (C * 4);
       const int n_units = 2 * SL * T;  // unit u: tile u / 16, entry half (u / 8) & 1, feature slab u % 8
-      auto entry_of = [&](int u) { return e0 + (u / SL) * KT + lane; };
-      auto unit_valid = [&](int u) { return u < n_units && entry_of(u) < e0 + n_here; };
-      auto issue_gather = [&](int u, int c, bool ok) {
-        const float* src = p.E + (size_t)c * D + (u % SL) * C;
+      auto idx_of = [&](int u) { return (u / SL) * KT + lane; };  // my entry of unit u, relative to e0
+      auto col_at = [&](int i) { return i < FRX_STAGE_CAP ? colS[i] : __ldg(p.col + beg + e0 + i); };
+      auto w_at = [&](int i) {
+        return i < FRX_STAGE_CAP ? wS[i] : (p.entry_w_e ? __ldg(p.entry_w_e + beg + e0 + i) : __ldg(p.entry_w + col_at(i)));
+      };
+      // One cp.async instruction moves F4 lanes x 16 bytes = the whole slab of 32 / F4 entries (measured: with
+      // lane = entry every instruction touched 32 different lines and the L1TEX tag stage, 70% busy, was the
+      // bound of the whole phase).  Lane group g = lane / F4 takes the entries EG g .. EG g + EG - 1 of the unit
+      // over the EG instructions, so its EG indices are contiguous in the staged array.
+      constexpr int EG = F4;                   // entries per lane group = cp.async instructions per unit
+      const int lg = lane / F4, lch = lane % F4;
+      auto issue_gather = [&](int u) {
+        const int ebase = (u / SL) * KT;
+        const float* slab_src = p.E + (u % SL) * C + 4 * lch;
+        int cidx[EG];
+        if (ebase + KT <= FRX_STAGE_CAP) {
+          const int4* cp4 = reinterpret_cast<const int4*>(colS + ebase + EG * lg);
 #pragma unroll
-        for (int j = 0; j < F4; ++j)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(gbase + ((((uint32_t)j ^ gkey) & (F4 - 1)) << 4)),
-                       "l"(src + 4 * j), "r"(ok ? 16 : 0)
+          for (int q4 = 0; q4 < EG / 4; ++q4) {
+            const int4 c4 = cp4[q4];
+            cidx[4 * q4] = c4.x; cidx[4 * q4 + 1] = c4.y; cidx[4 * q4 + 2] = c4.z; cidx[4 * q4 + 3] = c4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < EG; ++j) {
+            const int i = ebase + EG * lg + j;
+            cidx[j] = i < n_here ? __ldg(p.col + beg + e0 + i) : 0;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < EG; ++j) {
+          const int en = EG * lg + j;  // entry within the unit
+          const bool ok = ebase + en < n_here;
+          const uint32_t keyn = F4 == 8 ? (uint32_t)(en & 7) : (uint32_t)((en >> 1) & 3);
+          const uint32_t dst = gwarp + (uint32_t)en * (C * 4) + ((((uint32_t)lch ^ keyn) & (F4 - 1)) << 4);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst),
+                       "l"(slab_src + (size_t)(ok ? cidx[j] : 0) * D), "r"(ok ? 16 : 0)
                        : "memory");
+        }
         asm volatile("cp.async.commit_group;" ::: "memory");
       };
-      int c_1 = 0;        // index of the entry of unit u + STEP
-      float w_cur = 1.f;  // weight of the entry of unit u
-      if (warp < n_units) {
-        int c_0 = 0;
-        const bool ok0 = unit_valid(warp);
-        if (ok0) c_0 = __ldg(p.col + beg + entry_of(warp));
-        if (unit_valid(warp + STEP)) c_1 = __ldg(p.col + beg + entry_of(warp + STEP));
-        if (ok0 && item_side) w_cur = __ldg(p.entry_w + c_0);
-        issue_gather(warp, ok0 ? c_0 : 0, ok0);
-      }
+      if (warp < n_units) issue_gather(warp);
       for (int u = warp; u < n_units; u += STEP) {
         const int t = u / (2 * SL), w8 = u % SL;
         const int half = (u / SL) & 1;  // which 32 entries of the 64-entry tile
-        const int slab = w8 * C;  // first feature of this unit
-        const int e = entry_of(u);  // entry index within the row
-        const bool valid = e < e0 + n_here;
-        const float wgt = w_cur;
-        float4 v[F4];
+        const int ei = idx_of(u);       // my entry (lane = entry) of this unit
+        const int e = e0 + ei;          // ... within the row
+        const bool valid = ei < n_here;
+        float sq = 0.f, qw = 0.f;       // sqrt(s) * sc and q of my entry
+        if (valid) {
+          float s_ = 1.f, q_ = 1.f;
+          if (item_side) { s_ = w_at(ei); q_ = s_; }
+          if (e >= dup_lo && e < dup_hi) s_ *= 2.f;
+          sq = sqrtf(s_) * sc;
+          qw = q_;
+        }
+        float4 a[H4], b[H4];  // entries 2j and 2j+1, float4 columns 2m + o
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
 #pragma unroll
-        for (int j = 0; j < F4; ++j) {
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(v[j].x), "=f"(v[j].y), "=f"(v[j].z), "=f"(v[j].w)
-                       : "r"(gbase + ((((uint32_t)j ^ gkey) & (F4 - 1)) << 4))
-                       : "memory");
+        for (int m = 0; m < H4; ++m) {
+          const uint32_t a0 = grow0 + ((((uint32_t)(2 * m + o)) ^ key0) & (F4 - 1)) * 16u;
+          const uint32_t a1 = grow1 + ((((uint32_t)(2 * m + o)) ^ key1) & (F4 - 1)) * 16u;
+          if (F4 == 4 && o) {
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b[m].x), "=f"(b[m].y), "=f"(b[m].z), "=f"(b[m].w) : "r"(a1) : "memory");
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a[m].x), "=f"(a[m].y), "=f"(a[m].z), "=f"(a[m].w) : "r"(a0) : "memory");
+          } else {
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a[m].x), "=f"(a[m].y), "=f"(a[m].z), "=f"(a[m].w) : "r"(a0) : "memory");
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b[m].x), "=f"(b[m].y), "=f"(b[m].z), "=f"(b[m].w) : "r"(a1) : "memory");
+          }
 #ifdef FRX_EXP_NOLOAD
-          v[j] = make_float4(0.01f * e, 0.02f, 0.03f, 0.04f);
+          a[m] = make_float4(0.01f * e, 0.02f, 0.03f, 0.04f); b[m] = a[m];
 #endif
         }
-        {  // next unit's slab and weight, the index of the one after
-          const int u1 = u + STEP, u2 = u + 2 * STEP;
-          const bool ok1 = unit_valid(u1);
-          if (u1 < n_units) {
-            issue_gather(u1, ok1 ? c_1 : 0, ok1);
-            w_cur = (ok1 && item_side) ? __ldg(p.entry_w + c_1) : 1.f;
-          }
-          if (unit_valid(u2)) c_1 = __ldg(p.col + beg + entry_of(u2));
-        }
-        float sq = 0.f, qr = 0.f;
-        if (valid) {
-          float s = 1.f, q = 1.f;
-          if (item_side) { s = wgt; q = wgt; }
-          if (e >= dup_lo && e < dup_hi) s *= 2.f;
-          sq = sqrtf(s);
-          qr = s > 0.f ? q / sq : 0.f;
+        __syncwarp();  // every lane has its pair: the buffer may be refilled
+        if (u + STEP < n_units) issue_gather(u + STEP);  // next unit's slab
+        const float sq0 = __shfl_sync(0xffffffffu, sq, i0), sq1 = __shfl_sync(0xffffffffu, sq, i1);
+        const float q0 = __shfl_sync(0xffffffffu, qw, i0), q1 = __shfl_sync(0xffffffffu, qw, i1);
+        float rv[4 * H4];
+#pragma unroll
+        for (int m = 0; m < H4; ++m) {
+          rv[4 * m + 0] = fmaf(q1, b[m].x, q0 * a[m].x);
+          rv[4 * m + 1] = fmaf(q1, b[m].y, q0 * a[m].y);
+          rv[4 * m + 2] = fmaf(q1, b[m].z, q0 * a[m].z);
+          rv[4 * m + 3] = fmaf(q1, b[m].w, q0 * a[m].w);
         }
         const uint32_t gt = row_tile0 + (uint32_t)t;
         const int st = (int)(gt & 1u);
         const uint32_t use = gt >> 1;  // earlier tiles of this stage
         if (use > 0) mbar_wait(&empty_bar[st], (use - 1) & 1);  // stage free again
-        uint8_t* hi_tile = sm + st * L::kStageBytes;
-        uint8_t* lo_tile = hi_tile + L::kTileBytes;
-        // x = sqrt(s) e (fp32, as before); the operands are fp16 pairs hi = rn(x * sc), lo = rn(x * sc - hi)
-        // (fp16 has the 11 significand bits of tf32, so hi*hi + hi*lo + lo*hi is at least as accurate as 3xTF32
-        // while an MMA covers K = 16 instead of 8 and the operand tiles are half as large).  Adjacent lanes swap
-        // half of their features so that every lane stores entry PAIRS as 32-bit words: even lanes keep the
-        // features with (f & 4) == 0, odd lanes the others -> conflict-free under the 128B swizzle.
-        float rv[C];
-#pragma unroll
-        for (int j = 0; j < F4; ++j) {
-          v[j].x *= sq; v[j].y *= sq; v[j].z *= sq; v[j].w *= sq;
-          rv[4 * j + 0] = qr * v[j].x; rv[4 * j + 1] = qr * v[j].y; rv[4 * j + 2] = qr * v[j].z; rv[4 * j + 3] = qr * v[j].w;
-        }
-        const bool odd = (lane & 1) != 0;
-        const uint32_t wd = 16u * (uint32_t)half + (uint32_t)(lane >> 1);  // 32-bit word (entry pair) within the 128 B row
+        // byte offset of (feature row slab + 4o + t4, word 16 half + j) in the K-major 128B-swizzled tile; + 1024 m
+        const uint32_t wd = 16u * (uint32_t)half + (uint32_t)pj;
         const uint32_t wchunk = wd >> 2, wbyte = (wd & 3u) << 2;
+        uint8_t* hi_tile = sm + st * L::kStageBytes + ((uint32_t)(w8 * C) >> 3) * 1024u + wbyte;
+        uint32_t roff[4];
 #pragma unroll
-        for (int m = 0; m < F4 / 2; ++m) {
-          const float4 keep = odd ? v[2 * m + 1] : v[2 * m];
-          const float4 send = odd ? v[2 * m] : v[2 * m + 1];
-          float4 recv;
-          recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
-          recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
-          recv.z = __shfl_xor_sync(0xffffffffu, send.z, 1);
-          recv.w = __shfl_xor_sync(0xffffffffu, send.w, 1);
-          const float4 ev = odd ? recv : keep;  // entry 2j   (lower address)
-          const float4 od = odd ? keep : recv;  // entry 2j+1
-          const float e0v[4] = {ev.x * sc, ev.y * sc, ev.z * sc, ev.w * sc};
-          const float e1v[4] = {od.x * sc, od.y * sc, od.z * sc, od.w * sc};
+        for (int t4 = 0; t4 < 4; ++t4) {
+          const uint32_t r8 = (uint32_t)(4 * o + t4);
+          roff[t4] = (r8 << 7) + ((wchunk ^ r8) << 4);
+        }
+#pragma unroll
+        for (int m = 0; m < H4; ++m) {
+          const float xa[4] = {a[m].x * sq0, a[m].y * sq0, a[m].z * sq0, a[m].w * sq0};
+          const float xb[4] = {b[m].x * sq1, b[m].y * sq1, b[m].z * sq1, b[m].w * sq1};
 #pragma unroll
           for (int t4 = 0; t4 < 4; ++t4) {
-            const int mn = slab + 8 * m + (odd ? 4 : 0) + t4;
-            const __half2 hh = __floats2half2_rn(e0v[t4], e1v[t4]);
+            const __half2 hh = __floats2half2_rn(xa[t4], xb[t4]);  // low half = entry 2j (lower address)
             const float2 hf = __half22float2(hh);
-            const __half2 ll = __floats2half2_rn(e0v[t4] - hf.x, e1v[t4] - hf.y);
-            const uint32_t off = tile_chunk_off(mn, (int)wchunk) + wbyte;
+            const __half2 ll = __floats2half2_rn(xa[t4] - hf.x, xb[t4] - hf.y);
+            uint8_t* dst = hi_tile + 1024 * m + roff[t4];
 #ifdef FRX_EXP_NOSTORE
-            if (hf.x == 123.f) { *reinterpret_cast<__half2*>(hi_tile + off) = hh; *reinterpret_cast<__half2*>(lo_tile + off) = ll; }
+            if (hf.x == 123.f) { *reinterpret_cast<__half2*>(dst) = hh; *reinterpret_cast<__half2*>(dst + L::kTileBytes) = ll; }
 #else
-            *reinterpret_cast<__half2*>(hi_tile + off) = hh;
-            *reinterpret_cast<__half2*>(lo_tile + off) = ll;
+            *reinterpret_cast<__half2*>(dst) = hh;
+            *reinterpret_cast<__half2*>(dst + L::kTileBytes) = ll;
 #endif
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_bar[st]);
-        transpose_reduce<C>(rv, lane);
+        {  // column sums over the 16 lanes of equal parity: lane ends with local value index (lane >> 1) & (4 H4 - 1)
+          int cnt = 2 * H4;
+#pragma unroll
+          for (int off = 16; off >= 2; off >>= 1) {
+            const bool upper = (lane & off) != 0;
+            if (cnt >= 1) {
+#pragma unroll
+              for (int i = 0; i < 2 * H4; ++i) {
+                if (i < cnt) {
+                  const float send = upper ? rv[i] : rv[i + cnt];
+                  const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+                  rv[i] = (upper ? rv[i + cnt] : rv[i]) + recv;
+                }
+              }
+              cnt >>= 1;
+            } else {
+              rv[0] += __shfl_xor_sync(0xffffffffu, rv[0], off);
+            }
+          }
+        }
 #pragma unroll
         for (int q = 0; q < SL; ++q) rhs_acc[q] += (q == w8) ? rv[0] : 0.f;
       }
@@ -470,9 +535,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
     {
       // per-warp rhs partials go through the (now idle) staging area and are summed in a fixed order
       float* part = reinterpret_cast<float*>(sm) + warp * D;
-      if (warp != TC_MMA_WARP && (C == 32 || (lane & 1) == 0)) {
+      // the lane's feature within a slab (see the transpose-reduce of the loaders): local value k of parity o is
+      // feature 8 (k >> 2) + 4 o + (k & 3); at D = 128 lanes (lane >> 1) & 1 hold duplicates
+      const int kloc = C == 32 ? (lane >> 1) : ((lane >> 2) & 7);
+      const int fidx = 8 * (kloc >> 2) + 4 * (lane & 1) + (kloc & 3);
+      if (warp != TC_MMA_WARP && (C == 32 || ((lane >> 1) & 1) == 0)) {
 #pragma unroll
-        for (int q = 0; q < SL; ++q) part[q * C + (C == 32 ? lane : (lane >> 1))] = rhs_acc[q];
+        for (int q = 0; q < SL; ++q) part[q * C + fidx] = rhs_acc[q];
       }
     }
     __syncthreads();

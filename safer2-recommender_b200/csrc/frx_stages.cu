@@ -707,6 +707,12 @@ __global__ void __launch_bounds__(256) sum_d_kernel(const double* __restrict__ a
   if (threadIdx.x == 0) atomicAdd(out, s);
 }
 
+__global__ void __launch_bounds__(256) entry_weights_kernel(const int* __restrict__ col, const float* __restrict__ w,
+                                                            size_t e_begin, size_t e_end, float* __restrict__ ew) {
+  const size_t e = e_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < e_end) ew[e] = __ldg(w + __ldg(col + e));
+}
+
 // out[0] = max(out[0], bits(max |a[i]|)), out[1] likewise for w (non-negative floats compare like their bit patterns)
 __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ a, size_t n, const float* __restrict__ w,
                                                      size_t nw, unsigned* __restrict__ out) {
@@ -898,6 +904,12 @@ void launch_sum_d(const double* a, size_t n, double* out, cudaStream_t s, int nu
   if (launches) ++*launches;
 }
 
+void launch_entry_weights(const int* col, const float* w, size_t e_begin, size_t e_end, float* ew, cudaStream_t s,
+                          long long* launches) {
+  if (e_end <= e_begin) return;
+  entry_weights_kernel<<<(unsigned)((e_end - e_begin + 255) / 256), 256, 0, s>>>(col, w, e_begin, e_end, ew);
+  if (launches) ++*launches;
+}
 void launch_absmax(const float* E, size_t n, const float* w, size_t nw, unsigned* out, cudaStream_t s, int num_sms,
                    long long* launches) {
   cudaMemsetAsync(out, 0, 2 * sizeof(unsigned), s);
