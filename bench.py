@@ -239,7 +239,7 @@ def main():
     num_users, num_items, nnz = SHAPES[args.shape]
     cfg = dict(SAFER2_ML20M)
     cfg.update(model=args.model, dim=args.dim)
-    config = {"workload": f"SAFER2 d={args.dim} synthetic {args.shape} shape ({num_users} users x {num_items} items, "
+    config = {"workload": f"{args.model.upper()} d={args.dim} synthetic {args.shape} shape ({num_users} users x {num_items} items, "
                           f"~{nnz} nnz), use_snr=1 sampling_ratio=0.1 (BASELINE.json configs[2], README.md:79 flags)",
               "model_name": args.model, "dim": args.dim, "shape": args.shape,
               "l2_cache": "inputs_exceed_l2 (CSR+factors ~650 MB vs 126 MB L2); no explicit flush",
@@ -260,7 +260,7 @@ def main():
         v = float(np.mean(vals))
         res["value"] = v
         rows_all = int(np.unique(users).size + np.unique(items).size)
-        out = {"impl": "reference", "metric": "safer2_epoch_row_solves_per_s", "value": v, "unit": "row-solves/s",
+        out = {"impl": "reference", "metric": f"{args.model}_epoch_row_solves_per_s", "value": v, "unit": "row-solves/s",
                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                # epoch-equivalent time (the bounded sample scaled to the full workload), not the sample's own time
                "ms_per_step": 1e3 * rows_all / v, "sample_ms_per_step": 1e3 * res["sample_seconds"],
@@ -363,7 +363,8 @@ def main():
     R_u, R_i = ds.distinct_users, ds.distinct_items
     bytes_u = n_tuples * (4 * d + 4) + 4 * (num_users + 1) + 4 * R_u * d
     bytes_v = n_tuples * (4 * d + 4) + 4 * (num_items + 1) + 4 * R_i * d + 4 * n_tuples
-    t_rows = (stage_ms.get("step_U", 0.0) + stage_ms.get("step_V", 0.0)) * 1e-3
+    # (the block-subspace models run d / block_size block sweeps per side instead of one half-step)
+    t_rows = sum(stage_ms.get(k, 0.0) for k in ("step_U", "step_V", "block_U", "block_V")) * 1e-3
     peaks = measured_peaks()
     peak, peak_src = peaks["hbm_gbs"], peaks["source"]
     # TF32 dense peak: half the measured bf16 cuBLAS rate (same tensor datapath at half the K per instruction);
@@ -424,7 +425,7 @@ def main():
 
     if rank != 0:
         return
-    out = {"metric": "safer2_epoch_row_solves_per_s", "value": value, "unit": "row-solves/s", "n_gpus": world,
+    out = {"metric": f"{args.model}_epoch_row_solves_per_s", "value": value, "unit": "row-solves/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "epoch_s": ms_per_step * 1e-3,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": config, "clocks": clocks, "gpu_launches": int(launches),

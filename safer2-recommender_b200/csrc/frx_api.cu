@@ -1221,6 +1221,16 @@ static int stage_block(frx_model* m, const Csr* rows, bool user_side, float* X, 
   const float* other = user_side ? m->V : m->U;
   const int n_other = user_side ? m->num_items : m->num_users;
   const bool weighted = safer && !user_side;  // safer2pp.h:534-544: (z o U_B)^T U
+  if (c->world > 1 && !xmap) {
+    // Several ranks: the tuple-indexed prediction cache is replicated in memory, but only the entries of the rows
+    // a rank is about to solve have to be current.  They are recomputed from the (all-gathered) factors: the
+    // reference's incremental cache (ialspp.h:136-143) holds the same dot products up to fp32 rounding.
+    c->stage_begin("predict_rows");
+    launch_predict_chunks(rows->ptr, rows->col, rows->tup, rows->chunk_row, rows->chunk_off, rows->num_chunks,
+                          user_side ? m->U : m->V, nullptr, other, d, m->pred, c->stream, c->num_sms, &c->launches);
+    c->stage_end();
+    CK(cudaGetLastError());
+  }
   c->stage_begin(user_side ? "block_gramian_V" : "block_gramian_U");
   if (weighted) launch_norm_weights(m->z, m->hist_size, m->num_users, m->norm_w, c->stream, &c->launches);
   // strip G[bs:be, 0:d] = E_B^T (w o) E   (contains the B x B block, the reference's TODO ialspp.h:360-361)
@@ -1232,14 +1242,21 @@ static int stage_block(frx_model* m, const Csr* rows, bool user_side, float* X, 
              safer ? (user_side ? RM_PP_SAFER_U : RM_PP_SAFER_V) : RM_PP_IALS, bs, be - bs, m->pred};
   r = run_rows(m, rc);
   c->stage_end();
+  if (r) return r;
+  if (c->world > 1 && !xmap) {
+    // every rank needs the updated block before the other side's sweep (whole rows: the B columns are strided)
+    c->stage_begin("allgather_rows");
+    r = allgather_rows(c, X, (size_t)d, rows->rank_begin);
+    c->stage_end();
+  }
   return r;
 }
 
 static int stage_predict(frx_model* m, const Csr* rows, const float* U, const int* xmap) {
   frx_context* c = m->ctx;
   c->stage_begin("predict");
-  launch_predict(rows->ptr, rows->col, rows->tup, rows->order, rows->num_order, U, xmap, m->V, m->cfg.dim,
-                 m->pred, c->stream, &c->launches);
+  launch_predict_chunks(rows->ptr, rows->col, rows->tup, rows->chunk_row, rows->chunk_off, rows->num_chunks, U, xmap,
+                        m->V, m->cfg.dim, m->pred, c->stream, c->num_sms, &c->launches);
   c->stage_end();
   CK(cudaGetLastError());
   return FRX_OK;
@@ -1362,8 +1379,6 @@ extern "C" int frx_model_train(frx_model* m, frx_dataset* ds) {
     CK(cudaMemsetAsync(m->resid_dev, 0, sizeof(double) * 3 * kMaxResid, c->stream));
   }
   const int d = m->cfg.dim, B = m->cfg.block_size;
-  if (c->world > 1 && m->is_pp())
-    return fail(FRX_ERR_ARG, "iALS++ / SAFER2++ are single-GPU in this build (the tuple-indexed prediction cache is not sharded)");
   switch (m->cfg.model) {
     case FRX_IALS:  // ials.h:187-224
       RC(resid_snapshot(m, 0));
@@ -1456,6 +1471,7 @@ extern "C" int frx_model_train(frx_model* m, frx_dataset* ds) {
         RC(resid_record(m, 0, t));
         RC(resid_record(m, 1, t));
         RC(stage_item_gramian(m));
+        if (c->world > 1) RC(stage_predict(m, &ds->by_user, m->U, nullptr));  // the item sweeps of other ranks moved V
         RC(stage_user_loss(m, ds, m->G, m->pred));
         RC(stage_means(m));
       }

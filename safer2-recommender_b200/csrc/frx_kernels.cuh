@@ -168,6 +168,10 @@ void launch_user_loss(const LossParams& p, int user_begin, int user_end, cudaStr
 void launch_predict(const int* ptr, const int* col, const int* tup, const int* order, int num_rows,
                     const float* U, const int* xmap, const float* V, int d, float* pred,
                     cudaStream_t s, long long* launches);
+// the same over FRX_LOSS_CHUNK-entry chunks of the rows (balanced: long rows are spread over many warps)
+void launch_predict_chunks(const int* ptr, const int* col, const int* tup, const int* chunk_row, const int* chunk_off,
+                           int num_chunks, const float* U, const int* xmap, const float* V, int d, float* pred,
+                           cudaStream_t s, int num_sms, long long* launches);
 
 // z_u update (safer2.h:745-794, safer2pp.h:839-862, cvar_mf.h:597-642).
 // kind: 0 gaussian, 1 epanechnikov, 2 indicator.  only_with_history: skip rows with hist_size==0.

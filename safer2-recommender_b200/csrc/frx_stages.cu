@@ -393,6 +393,67 @@ __global__ void __launch_bounds__(128) user_loss_finish_kernel(LossParams p) {
   if (p.obs_sq) p.obs_sq[u] = obs;
 }
 
+// PredictDataset (ialspp.h:469-517) over FRX_LOSS_CHUNK-entry chunks of the rows (a popular item has tens of
+// thousands of entries: one warp per ROW leaves the launch waiting for a single warp): eight entries per pass,
+// pred[tup] = x_row . e_col.
+__global__ void __launch_bounds__(256) predict_chunks_kernel(const int* __restrict__ ptr, const int* __restrict__ col,
+                                                             const int* __restrict__ tup,
+                                                             const int* __restrict__ chunk_row,
+                                                             const int* __restrict__ chunk_off, int num_chunks,
+                                                             const float* __restrict__ U, const int* __restrict__ xmap,
+                                                             const float* __restrict__ V, int d,
+                                                             float* __restrict__ pred) {
+  extern __shared__ __align__(16) float sh[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* us = sh + warp * ((d + 3) & ~3);
+  for (int it = blockIdx.x * 8 + warp; it < num_chunks; it += gridDim.x * 8) {
+    const int u = chunk_row[it], off = chunk_off[it];
+    const int xr = xmap ? xmap[u] : u;
+    const int beg = ptr[u] + off;
+    const int n = min(FRX_LOSS_CHUNK, ptr[u + 1] - beg);
+    __syncwarp();
+    for (int k = lane; k < d; k += 32) us[k] = U[(size_t)xr * d + k];
+    __syncwarp();
+    int e = 0;
+    if ((d & 127) == 0) {
+      for (; e + 8 <= n; e += 8) {
+        const float* vp[8];
+        float acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          vp[q] = V + (size_t)__ldg(col + beg + e + q) * d;
+          acc[q] = 0.f;
+        }
+        for (int k = lane * 4; k < d; k += 128) {
+          const float4 u4 = *reinterpret_cast<const float4*>(us + k);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 v4 = __ldg(reinterpret_cast<const float4*>(vp[q] + k));
+            acc[q] = fmaf(v4.x, u4.x, acc[q]);
+            acc[q] = fmaf(v4.y, u4.y, acc[q]);
+            acc[q] = fmaf(v4.z, u4.z, acc[q]);
+            acc[q] = fmaf(v4.w, u4.w, acc[q]);
+          }
+        }
+        float mine = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float r = warp_sum(acc[q]);
+          if (lane == q) mine = r;
+        }
+        if (lane < 8) pred[__ldg(tup + beg + e + lane)] = mine;
+      }
+    }
+    for (; e < n; ++e) {
+      const float* v0 = V + (size_t)col[beg + e] * d;
+      float a0 = 0.f;
+      for (int k = lane; k < d; k += 32) a0 = fmaf(__ldg(v0 + k), us[k], a0);
+      a0 = warp_sum(a0);
+      if (lane == 0) pred[tup[beg + e]] = a0;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) predict_kernel(const int* __restrict__ ptr, const int* __restrict__ col,
                                                       const int* __restrict__ tup, const int* __restrict__ order,
                                                       int num_rows, const float* __restrict__ U,
@@ -824,6 +885,18 @@ void launch_predict(const int* ptr, const int* col, const int* tup, const int* o
   if (grid > 148 * 8) grid = 148 * 8;
   cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   predict_kernel<<<grid, 256, smem, s>>>(ptr, col, tup, order, num_rows, U, xmap, V, d, pred);
+  if (launches) ++*launches;
+}
+
+void launch_predict_chunks(const int* ptr, const int* col, const int* tup, const int* chunk_row, const int* chunk_off,
+                           int num_chunks, const float* U, const int* xmap, const float* V, int d, float* pred,
+                           cudaStream_t s, int num_sms, long long* launches) {
+  if (num_chunks <= 0) return;
+  const size_t smem = sizeof(float) * (size_t)(8 * ((d + 3) & ~3));
+  int grid = (num_chunks + 7) / 8;
+  if (grid > num_sms * 8) grid = num_sms * 8;
+  cudaFuncSetAttribute(predict_chunks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  predict_chunks_kernel<<<grid, 256, smem, s>>>(ptr, col, tup, chunk_row, chunk_off, num_chunks, U, xmap, V, d, pred);
   if (launches) ++*launches;
 }
 

@@ -38,7 +38,11 @@ def main():
              ("safer2", 256, dict(uobs_weight=0.002, reg=0.002, bandwidth=0.18, use_snr=1, sampling_ratio=0.1, snr_seed=1)),
              ("ials", 32, dict(uobs_weight=0.1, reg=0.003)),
              ("erm_mf", 32, dict(uobs_weight=0.004, reg=0.005)),
-             ("cvar_mf", 32, dict(uobs_weight=0.008, reg=0.002, stepsize=0.4))]
+             ("cvar_mf", 32, dict(uobs_weight=0.008, reg=0.002, stepsize=0.4)),
+             # block-subspace solvers: every rank refreshes the cached predictions of the rows it is about to solve
+             ("ialspp", 32, dict(uobs_weight=0.1, reg=0.003, block_size=8)),
+             ("safer2pp", 32, dict(uobs_weight=0.004, reg=0.004, bandwidth=0.15, block_size=8)),
+             ("safer2pp", 128, dict(uobs_weight=0.004, reg=0.004, bandwidth=0.15, block_size=64))]
     for name, d, cfg in cases:
         ds = pkg.Dataset(ctx, users, items)
         m = pkg.Model(ctx, nu, ni, model=name, dim=d, **cfg)

@@ -740,6 +740,34 @@ def test_generic_row_kernel_large_dims(pkg, O, ctx, name, cfg, d):
     ds.close()
 
 
+@pytest.mark.parametrize("name,cfg", [
+    ("ials", dict(uobs_weight=0.1, reg=0.003)),
+    ("erm_mf", dict(uobs_weight=0.004, reg=0.005)),
+])
+def test_msd_configuration_d512(pkg, O, ctx, name, cfg):
+    """BASELINE.json configs[3]: iALS / ERM-MF at d = 512 on MSD-like histories (log-normal, mean ~60 << d, a few
+    rows beyond 512 entries), a sub-sample of 1,500 users x 500 items: one epoch against the oracle."""
+    nu, ni = 1500, 500
+    rng = np.random.default_rng(77)
+    n_u = np.clip(np.round(np.exp(rng.normal(3.3, 1.0, nu))), 1, ni - 1).astype(np.int64)
+    n_u[:3] = (ni - 1, 300, 129)
+    users = np.repeat(np.arange(nu), n_u)
+    items = np.concatenate([rng.choice(ni, k, replace=False, p=None) for k in n_u])
+    perm = rng.permutation(users.shape[0])
+    users, items = users[perm].astype(np.int32), items[perm].astype(np.int32)
+    ods, om, ds, m = make_pair(pkg, O, ctx, users, items, nu, ni, model=name, dim=512, **cfg)
+    om.initialize(ods)
+    m.initialize(ds)
+    om.train(ods)
+    m.train(ds)
+    U, V = m.factors()
+    Uo, Vo = om.factors()
+    assert rel_fro(U, Uo) < FACTOR_TOL, rel_fro(U, Uo)
+    assert rel_fro(V, Vo) < FACTOR_TOL, rel_fro(V, Vo)
+    m.close()
+    ds.close()
+
+
 def _ref_cases():
     import importlib.util
     spec = importlib.util.spec_from_file_location("make_ref_golden", os.path.join(helpers.GOLDEN, "make_ref_golden.py"))
