@@ -562,17 +562,30 @@ static int ensure_eval_maps(frx_dataset* d) {
 #endif
 
 // All-gather of row blocks: rank k owns rows [rank_begin[k], rank_begin[k+1]) of X (row_floats floats
-// each) and every rank ends with all of them (collectives C2/C3/C4).  In place, as one
-// group of NCCL broadcasts because the blocks are balanced on work, not on row count.
+// each) and every rank ends with all of them (collectives C2/C3/C4).  In place.  The blocks are
+// balanced on work, not on row count, so this is not an ncclAllGather: every rank sends its block to every peer
+// and receives theirs, one group of point-to-point transfers through the NVSwitch (FRX_ALLGATHER=bcast selects
+// the round-1 formulation, a group of broadcasts, for comparison).
 static int allgather_rows(frx_context* c, float* X, size_t row_floats, const std::vector<int>& rank_begin) {
   if (c->world <= 1) return FRX_OK;
 #ifdef FRX_WITH_NCCL
+  static const bool use_bcast = []() { const char* e = getenv("FRX_ALLGATHER"); return e && !strcmp(e, "bcast"); }();
   NCK(ncclGroupStart());
-  for (int k = 0; k < c->world; ++k) {
-    const size_t b = rank_begin[k], e = rank_begin[k + 1];
-    if (e > b) {
-      float* blk = X + b * row_floats;
-      NCK(ncclBroadcast(blk, blk, (e - b) * row_floats, ncclFloat, k, c->comm, c->stream));
+  if (use_bcast) {
+    for (int k = 0; k < c->world; ++k) {
+      const size_t b = rank_begin[k], e = rank_begin[k + 1];
+      if (e > b) {
+        float* blk = X + b * row_floats;
+        NCK(ncclBroadcast(blk, blk, (e - b) * row_floats, ncclFloat, k, c->comm, c->stream));
+      }
+    }
+  } else {
+    const size_t mb = rank_begin[c->rank], me = rank_begin[c->rank + 1];
+    for (int s = 1; s < c->world; ++s) {
+      const int to = (c->rank + s) % c->world, from = (c->rank - s + c->world) % c->world;
+      if (me > mb) NCK(ncclSend(X + mb * row_floats, (me - mb) * row_floats, ncclFloat, to, c->comm, c->stream));
+      const size_t b = rank_begin[from], e = rank_begin[from + 1];
+      if (e > b) NCK(ncclRecv(X + b * row_floats, (e - b) * row_floats, ncclFloat, from, c->comm, c->stream));
     }
   }
   NCK(ncclGroupEnd());

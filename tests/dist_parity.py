@@ -43,6 +43,10 @@ def main():
              ("ialspp", 32, dict(uobs_weight=0.1, reg=0.003, block_size=8)),
              ("safer2pp", 32, dict(uobs_weight=0.004, reg=0.004, bandwidth=0.15, block_size=8)),
              ("safer2pp", 128, dict(uobs_weight=0.004, reg=0.004, bandwidth=0.15, block_size=64))]
+    only = os.environ.get("DIST_PARITY_CASES")  # e.g. "safer2:256,ialspp:32" (box time at N = 8 is charged 8x)
+    if only:
+        keep = {tuple(x.split(":")) for x in only.split(",")}
+        cases = [c for c in cases if (c[0], str(c[1])) in keep]
     for name, d, cfg in cases:
         ds = pkg.Dataset(ctx, users, items)
         m = pkg.Model(ctx, nu, ni, model=name, dim=d, **cfg)
