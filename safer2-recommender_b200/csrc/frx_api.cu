@@ -911,6 +911,15 @@ static int run_rows(frx_model* m, const RowCall& rc_) {
       launch_entry_weights(p.col, p.entry_w, (size_t)rw->h_ptr[rb], (size_t)rw->h_ptr[re], rw->ew, c->stream, &c->launches);
       p.entry_w_e = rw->ew;
     }
+    if (p.mode == RM_CVAR_U || p.mode == RM_CVAR_V) {
+      // gradient steps: G x for every row of the side being updated, as one GEMM ahead of the row kernel
+      const int nx = rc_.rows->nrows;
+      int r = c->ensure_wb_scratch((size_t)nx * p.d);
+      if (r) return r;
+      launch_rows_gemm(p.Xread, nx, p.d, p.G, c->wb_scratch, nullptr, nullptr, c->stream, &c->launches);
+      CK(cudaGetLastError());
+      p.Xg = c->wb_scratch;
+    }
     // rows with at most FRX_WB_MAX entries go to the dual-form kernel when the eigenbasis of G is at hand
     const bool use_wb = rc_.basis && rc_.basis->valid && rc_.rows->wb_num_groups > 0 && row_solve_wb_supported(p);
     const int direct_rows = use_wb ? rc_.rows->num_direct : rc_.rows->num_order;

@@ -37,6 +37,7 @@ struct RowParams {
   const float* Xread;  // where the current row is read from (CVaR V step reads pre-update copies)
   const int* xmap;     // row id -> row of X (fold-in evaluation), or null
   const float* G;      // [d x d] (weighted) Gramian of the fixed side
+  const float* Xg;     // tensor-core CVaR-MF gradient steps: Xread * G for all rows ([.. x d]), else null
   const float* entry_w;   // per fixed-side-row weight w_c = z_c/n_c (item side) or null
   const float* entry_w_e; // the same weights per history ENTRY (aligned with col: launch_entry_weights), or null
   const float* row_w;     // per-row dual weight z_u (user side) or null (= 1)

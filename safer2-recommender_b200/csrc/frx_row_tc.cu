@@ -99,7 +99,7 @@ __device__ __forceinline__ void tmem_init_system(const float* __restrict__ G, fl
   const int per_rb0 = rq + 1;                       // chunks with j <= i for M block 0
   const int total = NB == 2 ? 2 * rq + 6 : rq + 1;  // (rq + 1) + (4 + rq + 1)
   float4 gv[8];
-  if (G == nullptr) {  // clear only
+  if (G == nullptr && pieces == nullptr) {  // clear only
     uint32_t z[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) z[j] = 0u;
@@ -112,6 +112,11 @@ __device__ __forceinline__ void tmem_init_system(const float* __restrict__ G, fl
   }
   auto fetch = [&](int c) {
     const int rb = c < per_rb0 ? 0 : 1, ch = c < per_rb0 ? c : c - per_rb0;
+    if (G == nullptr) {  // gradient-step variant: the sum of the pieces only
+#pragma unroll
+      for (int it = 0; it < 8; ++it) gv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      return;
+    }
     const float* gblk = G + (size_t)(128 * rb + 32 * rq) * D + 32 * ch;
 #pragma unroll
     for (int it = 0; it < 8; ++it) gv[it] = __ldg(reinterpret_cast<const float4*>(gblk + (size_t)(it * 4 + (lane >> 3)) * D) + (lane & 7));
@@ -159,7 +164,9 @@ __device__ __forceinline__ void tmem_init_system(const float* __restrict__ G, fl
 
 // MODE 0: ordinary rows.  MODE 1: the piece launch (phase A only, partial sums dumped to
 // RowParams::piece_scratch).  MODE 2: long rows, started from the sum of their pieces (no gather).
-template <int D, int MODE>
+// GRAD: the CVaR-MF gradient steps (cvar_mf.h:88-180) instead of a solve: the SYRK sum alone goes to TMEM and
+// x <- x - step * (M x - rhs) is evaluated from it (see the gradient-step block below).
+template <int D, int MODE, bool GRAD = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p) {
   using L = TcLayout<D>;
   constexpr bool PIECE = MODE == 1, LONG = MODE == 2;
@@ -189,7 +196,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int mode = p.mode;
-  const bool item_side = (mode == RM_SAFER_V);
+  const bool item_side = (mode == RM_SAFER_V || mode == RM_CVAR_V);
   const bool is_row_warp = warp < P;   // warp w owns matrix rows 32w .. 32w+31
 
   if (tid == 0) {
@@ -224,7 +231,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
   {
     const float max_e = __uint_as_float(__ldg(p.syrk_absmax));
     const float max_w = __uint_as_float(__ldg(p.syrk_absmax + 1));
-    const float bound = (p.mode == RM_SAFER_V) ? max_e * sqrtf(2.f * max_w) : max_e;
+    const float bound = (p.mode == RM_SAFER_V || p.mode == RM_CVAR_V) ? max_e * sqrtf(2.f * max_w) : max_e;
     if (bound > 0.f && bound < 3.0e38f) {
       int ex;
       (void)frexpf(bound, &ex);  // bound = m * 2^ex, 0.5 <= m < 1
@@ -247,14 +254,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
       tmem_init_system<D>(nullptr, 0.f, 0.f, tmem_base, warp & 3, warp >> 2, 4, gbuf, lane);
     } else {
       const int r0 = p.order[blockIdx.x];
-      const RowScalars s0 = scaled_row_scalars(r0, p.ptr[r0 + 1] - p.ptr[r0]);
+      RowScalars s0 = scaled_row_scalars(r0, p.ptr[r0 + 1] - p.ptr[r0]);
+      if (GRAD) { s0.alpha = 0.f; s0.beta = 0.f; }
       if (LONG) {
         const int n0 = p.ptr[r0 + 1] - p.ptr[r0];
-        tmem_init_system<D>(p.G, s0.alpha, s0.beta, tmem_base, warp & 3, warp >> 2, 4, gbuf, lane,
+        tmem_init_system<D>(GRAD ? nullptr : p.G, s0.alpha, s0.beta, tmem_base, warp & 3, warp >> 2, 4, gbuf, lane,
                             p.piece_scratch + (size_t)p.row_piece0[r0] * p.piece_stride,
                             (n0 + FRX_PIECE - 1) / FRX_PIECE, p.piece_stride);
       } else {
-        tmem_init_system<D>(p.G, s0.alpha, s0.beta, tmem_base, warp & 3, warp >> 2, 4, gbuf, lane);
+        tmem_init_system<D>(GRAD ? nullptr : p.G, s0.alpha, s0.beta, tmem_base, warp & 3, warp >> 2, 4, gbuf, lane);
       }
     }
   }
@@ -560,7 +568,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
         for (int pc = 0; pc < npc; ++pc)
           b_reg += p.piece_scratch[(size_t)(pc_row + pc) * p.piece_stride + (p.piece_stride - D) + i];
       }
-      if (!PIECE) b_reg *= rs_row.bscale;
+      if (!PIECE && !GRAD) b_reg *= rs_row.bscale;
     }
     if (PIECE) {
       // ---- piece mode: dump the partial sums (lower chunks + rhs) and clear TMEM for the next piece ----
@@ -596,6 +604,76 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
     __syncthreads();
     tc_fence_after();
     FRX_DBG_LAP(1);  // rhs
+
+    if (GRAD) {
+      // ---- CVaR-MF gradient step (cvar_mf.h:88-180): x <- x - step * (M x - rhs) with the reference's
+      //      half-updated matrix M (B-3): its lower triangle carries the rank updates, the Gramian term is
+      //      complete, so  M x = cW * tril(S) x + cG * G x + reg * x.  tril(S) x comes from the TMEM-resident SYRK
+      //      sum (thread = row, panel by panel), G x from a GEMM over all rows ahead of the launch (RowParams::Xg).
+      //      User form (B-4: weight := stepsize, step := z_u): cW = s / n, cG = s * uw, rhs * s / n;
+      //      item form: cW = 1, cG = uw, step = s.
+      float* xS = wsum;  // [D]
+      float x_i = 0.f;
+      if (is_row_warp) {
+        x_i = p.Xread[(size_t)xr * D + 32 * warp + lane];
+        xS[32 * warp + lane] = x_i;
+      }
+      __syncthreads();
+      if (is_row_warp) {
+        const int i = 32 * warp + lane;
+        float acc0 = 0.f, acc1 = 0.f;
+        for (int pn = 0; pn <= warp; ++pn) {
+          uint32_t u[32];
+          FRX_TMEM_LD32(u, trow + 32u * (uint32_t)pn);
+          const int lim = pn < warp ? 32 : lane + 1;  // columns j <= i
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 x4 = reinterpret_cast<const float4*>(xS + 32 * pn)[c4];
+            if (4 * c4 + 0 < lim) acc0 = fmaf(__uint_as_float(u[4 * c4 + 0]), x4.x, acc0);
+            if (4 * c4 + 1 < lim) acc1 = fmaf(__uint_as_float(u[4 * c4 + 1]), x4.y, acc1);
+            if (4 * c4 + 2 < lim) acc0 = fmaf(__uint_as_float(u[4 * c4 + 2]), x4.z, acc0);
+            if (4 * c4 + 3 < lim) acc1 = fmaf(__uint_as_float(u[4 * c4 + 3]), x4.w, acc1);
+          }
+        }
+        const float tril = (acc0 + acc1) / sc2;
+        const float gx = __ldg(p.Xg + (size_t)xr * D + i);
+        float mx, rhs_i, step;
+        if (mode == RM_CVAR_U) {
+          const float reg = p.reg * (1.f + p.uw * (float)p.num_other);  // safer2.h:418-421
+          const float wgt = p.stepsize / (float)n;
+          mx = fmaf(wgt, tril, fmaf(p.stepsize * p.uw, gx, reg * x_i));
+          rhs_i = b_reg * wgt;
+          step = p.row_w ? p.row_w[r] : 1.f;
+        } else {
+          const float reg = p.reg * (p.item_reg[r] + p.alpha * p.uw * (float)p.num_users_total);  // safer2.h:426-432
+          mx = tril + fmaf(p.uw, gx, reg * x_i);
+          rhs_i = b_reg;
+          step = p.stepsize;
+        }
+        p.X[(size_t)xr * D + i] = x_i - step * (mx - rhs_i);
+      }
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      // TMEM for this CTA's next item: zeros, or the sum of the pieces of a long row
+      if (ri_next < p.num_rows) {
+        if (LONG) {
+          const int rn = p.order[ri_next];
+          const int nn = p.ptr[rn + 1] - p.ptr[rn];
+          tmem_init_system<D>(nullptr, 0.f, 0.f, tmem_base, warp & 3, warp >> 2, 4, gbuf, lane,
+                              p.piece_scratch + (size_t)p.row_piece0[rn] * p.piece_stride,
+                              (nn + FRX_PIECE - 1) / FRX_PIECE, p.piece_stride);
+        } else {
+          tmem_init_system<D>(nullptr, 0.f, 0.f, tmem_base, warp & 3, warp >> 2, 4, gbuf, lane);
+        }
+      }
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      FRX_DBG_LAP(5);
+      ri = ri_next;
+      continue;
+    }
 
     // ---- blocked Cholesky, 32-wide panels ----
 #pragma unroll 1
@@ -897,17 +975,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
 size_t row_solve_tc_piece_floats(int d) { return (size_t)(d == 256 ? 36 : 10) * 1024 + (size_t)d; }
 
 bool row_solve_tc_supported(const RowParams& p) {
-  const bool mode_ok = p.mode == RM_IALS || p.mode == RM_SAFER_U || p.mode == RM_SAFER_V;
+  const bool mode_ok = p.mode == RM_IALS || p.mode == RM_SAFER_U || p.mode == RM_SAFER_V || p.mode == RM_CVAR_U ||
+                       p.mode == RM_CVAR_V;
   return mode_ok && p.cs == 0 && p.bd == p.d && (p.d == 128 || p.d == 256);
 }
 
-template <int D, int MODE>
+template <int D, int MODE, bool GRAD>
 static void launch_tc_instance(const RowParams& p, int work, cudaStream_t s, int num_sms) {
   cudaMemsetAsync(p.work_counter, 0, sizeof(int), s);
   const int smem = TcLayout<D>::kTotal + 1024;
-  cudaFuncSetAttribute(row_solve_tc_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(row_solve_tc_kernel<D, MODE, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int grid = num_sms < work ? num_sms : work;
-  row_solve_tc_kernel<D, MODE><<<grid, TC_THREADS, smem, s>>>(p);
+  row_solve_tc_kernel<D, MODE, GRAD><<<grid, TC_THREADS, smem, s>>>(p);
+}
+
+template <int D>
+static void launch_tc_dim(const RowParams& p, int work, cudaStream_t s, int num_sms) {
+  const bool grad = p.mode == RM_CVAR_U || p.mode == RM_CVAR_V;
+  if (p.piece_mode == 1) launch_tc_instance<D, 1, false>(p, work, s, num_sms);  // the piece sums are the same
+  else if (p.piece_mode == 2) { if (grad) launch_tc_instance<D, 2, true>(p, work, s, num_sms); else launch_tc_instance<D, 2, false>(p, work, s, num_sms); }
+  else { if (grad) launch_tc_instance<D, 0, true>(p, work, s, num_sms); else launch_tc_instance<D, 0, false>(p, work, s, num_sms); }
 }
 
 // p.piece_mode: 0 ordinary rows (p.order / p.num_rows), 1 pieces (p.piece_* / p.num_pieces),
@@ -915,15 +1002,8 @@ static void launch_tc_instance(const RowParams& p, int work, cudaStream_t s, int
 void launch_row_solve_tc(const RowParams& p, cudaStream_t s, int num_sms, long long* launches) {
   const int work = p.piece_mode == 1 ? p.num_pieces : p.num_rows;
   if (work <= 0) return;
-  if (p.d == 256) {
-    if (p.piece_mode == 1) launch_tc_instance<256, 1>(p, work, s, num_sms);
-    else if (p.piece_mode == 2) launch_tc_instance<256, 2>(p, work, s, num_sms);
-    else launch_tc_instance<256, 0>(p, work, s, num_sms);
-  } else {
-    if (p.piece_mode == 1) launch_tc_instance<128, 1>(p, work, s, num_sms);
-    else if (p.piece_mode == 2) launch_tc_instance<128, 2>(p, work, s, num_sms);
-    else launch_tc_instance<128, 0>(p, work, s, num_sms);
-  }
+  if (p.d == 256) launch_tc_dim<256>(p, work, s, num_sms);
+  else launch_tc_dim<128>(p, work, s, num_sms);
   if (launches) ++*launches;
 }
 

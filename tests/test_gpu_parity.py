@@ -265,6 +265,9 @@ def test_fixture_train_and_evaluate(pkg, O, ctx, name, cfg, dim):
     ("ials", dict(uobs_weight=0.1, reg=0.003)),
     ("safer2", dict(uobs_weight=0.004, reg=0.004, bandwidth=0.15)),
     ("erm_mf", dict(uobs_weight=0.004, reg=0.005)),
+    # gradient-step variant of the kernel (the SYRK sum alone in TMEM, x - step * (M x - rhs) from it); the second
+    # epoch has z in {0, 1} (B-4: users below the VaR do not move)
+    ("cvar_mf", dict(uobs_weight=0.008, reg=0.002, stepsize=0.4)),
 ])
 def test_tensor_core_row_kernel_epoch(pkg, O, ctx, name, cfg, d):
     """d = 128 / 256 take the tcgen05 path (3xTF32 SYRK in TMEM): one epoch must still agree
@@ -277,13 +280,17 @@ def test_tensor_core_row_kernel_epoch(pkg, O, ctx, name, cfg, d):
     ods, om, ds, m = make_pair(pkg, O, ctx, users, items, nu, ni, model=name, dim=d, **cfg)
     om.initialize(ods)
     m.initialize(ds)
-    om.train(ods)
-    m.train(ds)
+    for _ in range(2 if name == "cvar_mf" else 1):
+        om.train(ods)
+        m.train(ds)
     U, V = m.factors()
     Uo, Vo = om.factors()
     so, sg = om.state(), m.state()
     assert rel_fro(U, Uo) < FACTOR_TOL, rel_fro(U, Uo)
     assert rel_fro(V, Vo) < FACTOR_TOL, rel_fro(V, Vo)
+    if name == "cvar_mf":
+        assert abs(sg["xi"] - so["xi"]) < 1e-4
+        assert np.array_equal(sg["z"], so["z"])
     # per-row check as well: no single row may be far off
     rowerr = np.linalg.norm(U - Uo, axis=1) / np.maximum(np.linalg.norm(Uo, axis=1), 1e-12)
     assert rowerr.max() < 1e-3, (int(rowerr.argmax()), float(rowerr.max()))
@@ -348,6 +355,8 @@ def test_dual_form_rows_match_the_oracle(pkg, O, ctx, name, cfg, d):
     ("safer2", dict(uobs_weight=0.05, reg=0.05, bandwidth=0.15), 256, "item"),   # the bench's case: SAFER2-V, d = 256, stale tail
     ("ials", dict(uobs_weight=0.1, reg=0.05), 256, "item"),
     ("safer2", dict(uobs_weight=0.05, reg=0.05, bandwidth=0.15), 128, "user"),
+    ("cvar_mf", dict(uobs_weight=0.05, reg=0.05, stepsize=0.01), 256, "item"),  # gradient step from the piece sums
+    ("cvar_mf", dict(uobs_weight=0.05, reg=0.05, stepsize=0.01), 128, "user"),
 ])
 def test_tensor_core_long_rows_are_split(pkg, O, ctx, name, cfg, d, long_side):
     """Rows with more than 2048 entries take the piece path of the tensor-core kernel (partial SYRK
