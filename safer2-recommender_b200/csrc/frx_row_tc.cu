@@ -62,7 +62,7 @@ struct TcLayout {
   // phase A: per loader warp one gather buffer (32 lanes x D/8 floats) that cp.async fills one unit ahead; it
   // lies behind the operand stages and is aliased by the L panels of phase B
   static constexpr int kGatherOff = kStagingBytes;
-  static constexpr int kGatherWarpBytes = 32 * (D / 8) * 4;
+  static constexpr int kGatherWarpBytes = 32 * 128;  // 32 entries x one 128 B slab
   // ... followed by the staged indices and weights of the work item's history entries (also phase A only)
   static constexpr int kIdxOff = kGatherOff + (TC_LOADER_WARPS - 1) * kGatherWarpBytes;
   static constexpr int kPhaseA = kIdxOff + 2 * FRX_STAGE_CAP * 4;
@@ -171,8 +171,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
   using L = TcLayout<D>;
   constexpr bool PIECE = MODE == 1, LONG = MODE == 2;
   constexpr int P = L::P;
-  constexpr int F4 = D / 32;   // float4 loads per loader lane
-  constexpr int C = 4 * F4;    // floats per loader lane
+  constexpr int F4 = 8;        // float4 columns of a loader unit: a 128 B slab (one line) per history entry
+  constexpr int C = 4 * F4;    // features per unit
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the swizzled tiles, by pointer arithmetic on the shared array itself: an
   // integer round trip makes the compiler lose the address space and emit generic LD/ST for every access.
@@ -200,8 +200,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
   const bool is_row_warp = warp < P;   // warp w owns matrix rows 32w .. 32w+31
 
   if (tid == 0) {
-    mbar_init(&full_bar[0], 2 * 8);  // units of a 64-entry tile: 2 entry halves x 8 feature slabs
-    mbar_init(&full_bar[1], 2 * 8);
+    mbar_init(&full_bar[0], 2 * (D / 32));  // units of a 64-entry tile: 2 entry halves x D / 32 feature slabs
+    mbar_init(&full_bar[1], 2 * (D / 32));
     mbar_init(&empty_bar[0], 1);
     mbar_init(&empty_bar[1], 1);
     mbar_init(acc_bar, 1);
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
     }
     __syncthreads();
     const uint32_t row_tile0 = tile_base;  // CTA-wide index of this row's first tile: stage = index & 1
-    constexpr int SL = D / C;              // 32-entry x C-feature units per tile (8)
+    constexpr int SL = D / C;              // feature slabs: (32-entry x 32-feature) units per 32 entries (8 or 4)
     float rhs_acc[SL];
 #pragma unroll
     for (int q = 0; q < SL; ++q) rhs_acc[q] = 0.f;
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) row_solve_tc_kernel(RowParams p
       const uint32_t key0 = F4 == 8 ? (uint32_t)(i0 & 7) : (uint32_t)(pj & 3);
       const uint32_t key1 = F4 == 8 ? (uint32_t)(i1 & 7) : (uint32_t)(pj & 3);
       const uint32_t grow0 = gwarp + (uint32_t)i0 * (C * 4), grow1 = gwarp + (uint32_t)i1 * (C * 4);
-      const int n_units = 2 * SL * T;  // unit u: tile u / 16, entry half (u / 8) & 1, feature slab u % 8
+      const int n_units = 2 * SL * T;  // unit u: tile u / (2 SL), entry half (u / SL) & 1, feature slab u % SL
       auto idx_of = [&](int u) { return (u / SL) * KT + lane; };  // my entry of unit u, relative to e0
       auto col_at = [&](int i) { return i < FRX_STAGE_CAP ? colS[i] : __ldg(p.col + beg + e0 + i); };
       auto w_at = [&](int i) {
