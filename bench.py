@@ -403,12 +403,14 @@ def main():
     }
     traffic, traffic_src = profile_traffic(args, world, cfg)
     roofline = {"bound": "hbm", "kernel": "row kernels (step_U + step_V launches: CSR gather + SYRK + solve; direct d x d "
-                                          "Cholesky for rows > 128 entries, dual form for the rest)",
+                                          "Cholesky for rows > 128 entries, dual form for the rest; fp32 accuracy "
+                                          "from fp16 / tf32 hi+lo operand pairs with fp32 accumulation)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_epoch": bytes_u + bytes_v,
                 # the same launches against the tensor roofline: flops of the REFERENCE's algorithm (lower-triangle SYRK
-                # + one d x d Cholesky per row); the 3xTF32 scheme issues three MMA passes per SYRK flop, the dual form
+                # + one d x d Cholesky per row); the error-compensated operands (fp16 hi/lo pairs in the direct kernel's
+                # SYRK, tf32 hi/lo elsewhere) issue three MMA passes per useful flop, the dual form
                 # executes fewer flops than the reference's algorithm for the rows it serves
                 "tensor": {"useful_tflops": useful_tf, "peak_tflops_tf32": tf32_peak,
                            "peak_source": "0.5 x bf16_tflops_sustained of MEASURED_PEAKS.json" if peaks["measured"]

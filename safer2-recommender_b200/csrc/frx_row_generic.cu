@@ -26,7 +26,9 @@ struct SmemLayout {
     dp = (bd + 3) & ~3;
     int dx = (d + 3) & ~3;
     chunk_off = 0;
-    qr_off = chunk_off + CH * dp;
+    // the gather chunk [CH][dp]; the blocked Cholesky of the global-scratch case reuses it as its column-major
+    // panel [32][dp + 8] (CH == 32)
+    qr_off = chunk_off + CH * (dp + 8);
     colk_off = qr_off + CH;
     ldiag_off = colk_off + dp + 4;
     xv_off = ldiag_off + dp;
@@ -354,6 +356,117 @@ __global__ void __launch_bounds__(NT_MAX) row_solve_generic_kernel(RowParams p) 
     }
 
     // ---- Cholesky of the augmented system (rows 0..dp; row dp carries rhs -> y) -----
+    if (!p.use_smem_matrix) {
+      // The system lives in global scratch (d = 512: 525 KB): blocked right-looking factorisation, 32-wide panels
+      // staged in shared memory (column-major: Pt[c * PS + (i - p0)]), so that every trailing element is read and
+      // written once per PANEL with 32 FMAs in between instead of once per column (measured at the MSD shape,
+      // d = 512: the unblocked sweep below moved ~360 MB through L2 per row and took 9.6 ms per row).
+      float* Pt = chunk;
+      const int PS = dp + 8;
+      for (int p0 = 0; p0 < dp; p0 += 32) {
+        const int nb = min(32, dp - p0);
+        const int nrows = dp + 1 - p0;  // panel rows p0 .. dp (row dp: the rhs)
+        for (int idx = tid; idx < nrows * nb; idx += NT) {
+          const int ii = idx / nb, c = idx - ii * nb;
+          const int i = p0 + ii;
+          Pt[c * PS + ii] = (p0 + c <= i) ? Mtx[tri(i) + p0 + c] : 0.f;
+        }
+        __syncthreads();
+        if (warp == 0) {  // diagonal block in registers: lane = row, column k broadcast by shuffles
+          float a[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) a[c] = (c < nb && lane < nb) ? Pt[c * PS + lane] : (c == lane ? 1.f : 0.f);
+          bool bad = false;
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            float pivot = __shfl_sync(0xffffffffu, a[k], k);
+            if (!(pivot > 0.f)) { bad = bad || k < nb; pivot = 1.f; }
+            const float l = sqrtf(pivot);
+            const float lk = lane == k ? l : a[k] / l;  // L[lane][k] (lanes >= k)
+            a[k] = lk;
+#pragma unroll
+            for (int j = k + 1; j < 32; ++j) {
+              const float ljk = __shfl_sync(0xffffffffu, lk, j);
+              if (lane >= j) a[j] = fmaf(-lk, ljk, a[j]);
+            }
+            if (lane == k && k < nb) ldiag[p0 + k] = l;
+          }
+          if (bad && lane == 0) atomicExch(p.status, 1);
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (c < nb && lane < nb && c <= lane) Pt[c * PS + lane] = a[c];
+        }
+        __syncthreads();
+        for (int ii = nb + tid; ii < nrows; ii += NT) {  // rows below: L21 row = A21 row * L11^-T (thread = row)
+          float x[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) x[c] = c < nb ? Pt[c * PS + ii] : 0.f;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            if (c < nb) {
+              x[c] = x[c] / Pt[c * PS + c];
+#pragma unroll
+              for (int m2 = c + 1; m2 < 32; ++m2)
+                if (m2 < nb) x[m2] = fmaf(-x[c], Pt[c * PS + m2], x[m2]);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (c < nb) Pt[c * PS + ii] = x[c];
+        }
+        __syncthreads();
+        for (int idx = tid; idx < nrows * nb; idx += NT) {  // the factor goes back to the packed matrix
+          const int ii = idx / nb, c = idx - ii * nb;
+          const int i = p0 + ii;
+          if (p0 + c <= i && !(ii < nb && c == ii)) Mtx[tri(i) + p0 + c] = Pt[c * PS + ii];
+        }
+        const int p1 = p0 + nb, rem = dp - p1;  // trailing rows / columns p1 .. dp-1 (a multiple of 4), then the rhs row
+        const int Tn = rem >> 2, ntl = (Tn * (Tn + 1)) >> 1;
+        for (int t = tid; t < ntl; t += NT) {
+          int ti = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+          while (tri(ti + 1) <= t) ++ti;
+          while (tri(ti) > t) --ti;
+          const int tj = t - tri(ti);
+          float acc[4][4], old[4][4];
+          // the old values are requested first: their L2 latency passes under the 32 panel columns below
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const float* mrow = Mtx + tri(p1 + 4 * ti + a) + p1 + 4 * tj;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              acc[a][b] = 0.f;
+              old[a][b] = (4 * tj + b <= 4 * ti + a) ? mrow[b] : 0.f;
+            }
+          }
+          const float* pa = Pt + nb + 4 * ti;
+          const float* pb = Pt + nb + 4 * tj;
+          for (int c = 0; c < nb; ++c) {
+            const float4 a4 = *reinterpret_cast<const float4*>(pa + c * PS);
+            const float4 b4 = *reinterpret_cast<const float4*>(pb + c * PS);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+              for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+          }
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const int i = p1 + 4 * ti + a;
+            float* mrow = Mtx + tri(i) + p1 + 4 * tj;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+              if (4 * tj + b <= 4 * ti + a) mrow[b] = old[a][b] - acc[a][b];
+          }
+        }
+        for (int j = tid; j < rem; j += NT) {  // rhs row (row dp of the augmented system)
+          float a = 0.f;
+          for (int c = 0; c < nb; ++c) a = fmaf(Pt[c * PS + (dp - p0)], Pt[c * PS + nb + j], a);
+          rhs[p1 + j] -= a;
+        }
+        __syncthreads();
+      }
+    } else
     for (int k = 0; k < dp; ++k) {
       float pivot = Mtx[tri(k) + k];
       if (!(pivot > 0.f)) {
@@ -376,8 +489,40 @@ __global__ void __launch_bounds__(NT_MAX) row_solve_generic_kernel(RowParams p) 
       }
       __syncthreads();
     }
-    // ---- back substitution L^T x = y (one warp) ---------------------------------------
-    if (warp == 0) {
+    // ---- back substitution L^T x = y ---------------------------------------
+    if (!p.use_smem_matrix) {
+      // blocked like the factorisation: the 32 rows of a panel are staged in shared memory by all threads (one
+      // global latency per panel instead of one per row), warp 0 solves the 32 x 32 triangle, then every thread
+      // applies the panel's 32 solved unknowns to one earlier component
+      float* S = chunk;  // [32][PS] row-major: S[(k - p0) * PS + j] = L[k][j], j <= k
+      const int PS = dp + 8;
+      for (int j = tid; j < dp; j += NT) sol[j] = rhs[j];
+      __syncthreads();
+      for (int p0 = ((dp - 1) / 32) * 32; p0 >= 0; p0 -= 32) {
+        const int nb = min(32, dp - p0);
+        for (int kk = warp; kk < nb; kk += NW) {
+          const float* mrow = Mtx + tri(p0 + kk);
+          for (int j = lane; j < p0 + kk; j += 32) S[kk * PS + j] = mrow[j];
+        }
+        __syncthreads();
+        if (warp == 0) {
+          for (int kk = nb - 1; kk >= 0; --kk) {
+            const float xk = sol[p0 + kk] / ldiag[p0 + kk];
+            __syncwarp();
+            if (lane == kk) sol[p0 + kk] = xk;
+            else if (lane < kk) sol[p0 + lane] = fmaf(-S[kk * PS + p0 + lane], xk, sol[p0 + lane]);
+            __syncwarp();
+          }
+        }
+        __syncthreads();
+        for (int j = tid; j < p0; j += NT) {
+          float a = 0.f;
+          for (int kk = 0; kk < nb; ++kk) a = fmaf(S[kk * PS + j], sol[p0 + kk], a);
+          sol[j] -= a;
+        }
+        __syncthreads();
+      }
+    } else if (warp == 0) {
       for (int j = lane; j < dp; j += 32) sol[j] = rhs[j];
       __syncwarp();
       for (int k = dp - 1; k >= 0; --k) {
