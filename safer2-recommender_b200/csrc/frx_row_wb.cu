@@ -66,7 +66,7 @@ struct WbSet {  // per solver set / accumulator slot (a multiple of 1024 bytes: 
   float y1[128];        // forward-substitution result of each panel
   float rd[4][32];      // reciprocal diagonal of each factored block
   float rs[4][32];      // residuals of the panel being back-substituted
-  float corr[4][4][32]; // back substitution: [producer slot][target slot] L^T y contributions
+  float corr[4][3][32]; // back substitution: [producer slot][target slot < producer] L^T y contributions
 };
 
 template <int D>
@@ -76,7 +76,8 @@ struct WbLayout {
   static constexpr int kSetOff = WB_NSTAGE * WB_STAGE_BYTES;
   static constexpr int kRingOff = kSetOff + WB_NACC * (int)sizeof(WbSet);
   static constexpr int kSdOff = ((kRingOff + WB_RING * (int)sizeof(WbRing) + 15) / 16) * 16;
-  static constexpr int kBarOff = ((kSdOff + WB_NLOADER * 64 * 4 + 15) / 16) * 16;
+  static constexpr int kGbOff = ((kSdOff + WB_NLOADER * 64 * 4 + 127) / 128) * 128;  // gather buffers, 4 KB per loader warp
+  static constexpr int kBarOff = kGbOff + WB_NLOADER * 4096;
   static constexpr int kNumBars = 2 * WB_NSTAGE + 4 * WB_NACC + 2 * WB_RING;
   static constexpr int kTotal = kBarOff + kNumBars * 8;
 };
@@ -186,16 +187,34 @@ __global__ void __launch_bounds__(WB_THREADS, 1) row_solve_wb_kernel(RowParams p
           if (p.mode == RM_SAFER_V) { const float w = __ldg(p.entry_w + c); sw = w; qw = w; }
         }
         const float sq = sqrtf(sw);
-        const float4* src = reinterpret_cast<const float4*>(q.Et + (size_t)c * D);
         const float* lrow = q.lsub + (size_t)(desc >= 0 ? (desc >> 2) : 0) * D;
         const float* rrow = q.rsd + (size_t)(desc >= 0 ? (desc >> 2) : 0) * D;
-        float4 v[8];
+        // The 32-feature chunk of the 32 entries travels by LINE-coalesced cp.async into this warp's gather
+        // buffer (8 lanes per 128 B line: with lane = entry every load instruction touched 32 different lines and
+        // the L1TEX tag stage ran at 71 %), XOR-swizzled, and is read back with lane = entry; chunk k+1 is in
+        // flight while chunk k runs through the recurrence.
+        const uint32_t gb = sm_addr + L::kGbOff + (uint32_t)lw * 4096u;
+        const int lg = lane >> 3, lch = lane & 7;
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        int cidx[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cidx[j] = __shfl_sync(0xffffffffu, c, 8 * lg + j);
+        auto issue_chunk = [&](int k) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int en = 8 * lg + j;
+            const bool ok = (vmask >> en) & 1u;
+            const float* srcp = q.Et + (size_t)(ok ? cidx[j] : 0) * D + 32 * k + 4 * lch;
+            const uint32_t dst = gb + (uint32_t)en * 128u + ((uint32_t)(lch ^ (en & 7)) << 4);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(srcp), "r"(ok ? 16 : 0) : "memory");
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        };
         float lnext = 0.f, rnext = 0.f;
         if (desc >= 0) {
           lnext = __ldg(lrow + lane);
           rnext = __ldg(rrow + lane);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = valid ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          issue_chunk(0);
         }
         float wprev = 0.f;  // w_(j-1) of the recurrence, carried across chunks
         for (int k = 0; k < KC; ++k) {
@@ -207,15 +226,19 @@ __global__ void __launch_bounds__(WB_THREADS, 1) row_solve_wb_kernel(RowParams p
             sd[lane] = lnext;
             sd[32 + lane] = rnext;
             float4 vc[8];
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) vc[j] = v[j];
+            for (int j = 0; j < 8; ++j)
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(vc[j].x), "=f"(vc[j].y), "=f"(vc[j].z), "=f"(vc[j].w)
+                           : "r"(gb + (uint32_t)lane * 128u + ((uint32_t)(j ^ (lane & 7)) << 4))
+                           : "memory");
+            __syncwarp();  // every lane has its chunk: the buffer may be refilled
             if (k + 1 < KC) {  // next chunk in flight while this one is processed
               lnext = __ldg(lrow + 32 * (k + 1) + lane);
               rnext = __ldg(rrow + 32 * (k + 1) + lane);
-              if (valid) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = __ldg(src + 8 * (k + 1) + j);
-              }
+              issue_chunk(k + 1);
             }
             __syncwarp();
             uint8_t* hi_tile = sm + st * WB_STAGE_BYTES;
