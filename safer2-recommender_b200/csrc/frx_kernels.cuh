@@ -73,7 +73,8 @@ struct RowParams {
   size_t piece_stride;
 };
 // (The piece length also bounds the accumulation chain inside the tensor cores, whose fp32 accumulator rounds
-// toward zero: 128 MMA steps per TMEM pass keep that bias near 4e-6; the pieces are added with IEEE fp32 adds.)
+// toward zero: 64 K-steps of 16 entries per TMEM pass keep that bias near 4e-6; the pieces are added with IEEE
+// fp32 adds.)
 constexpr int FRX_STAGE_CAP = 1792;  // history entries of a work item whose indices / weights the tensor-core row kernel stages
 constexpr int FRX_SPLIT_MIN = FRX_STAGE_CAP;
 constexpr int FRX_PIECE = 1024;

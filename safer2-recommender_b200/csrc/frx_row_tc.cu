@@ -7,12 +7,14 @@
 //            warps that are idle during the back substitution of the previous row (row_scalars,
 //            tmem_init_system).
 //   phase A  S_r = sum_c s_c e_c e_c^T  (+ rhs = sum_c q_c e_c)
-//            15 loader warps take (32-entry tile, 32-feature slab) units round-robin: lane = history
-//            entry (128 B per lane per unit), split each fp32 into tf32 hi + lo and store them
-//            TRANSPOSED into K-major, 128B-swizzled operand tiles [feature][32 entries]; warp 15 issues
-//            tcgen05.mma kind::tf32 for hi*hi + hi*lo + lo*hi (error-compensated 3xTF32: fp32-level
-//            accuracy) onto the TMEM accumulators; lower-triangle M blocks only.  Two operand stages,
-//            mbarrier full/empty pipeline, tcgen05.commit frees a stage.
+//            The indices / weights of the row are staged in shared memory; 15 loader warps take
+//            (32-entry, 32-feature) units round-robin: the unit's 128-byte slabs arrive by line-coalesced
+//            cp.async in a swizzled per-warp buffer one unit ahead, are read back as entry PAIRS, scaled
+//            by a power of two and written as fp16 hi + lo words into K-major, 128B-swizzled operand tiles
+//            [feature][64 entries]; warp 15 issues tcgen05.mma kind::f16 for hi*hi + hi*lo + lo*hi (the
+//            11 + 11 significand bits of an error-compensated 3xTF32 product at twice the K per MMA and
+//            half the operand bytes: fp32-level accuracy) onto the TMEM accumulators; lower-triangle M
+//            blocks only.  Two operand stages, mbarrier full/empty pipeline, tcgen05.commit frees a stage.
 //   phase B  right-looking blocked Cholesky in TMEM with 32-wide panels.  Thread i owns matrix row i
 //            (tcgen05.ld gives it its 32 panel entries): the diagonal 32x32 block is factored by one
 //            warp (columns published through shared memory, shuffle shortcut for the next pivot); the
@@ -23,15 +25,17 @@
 //            sweep; the back substitution is column-oriented over the L panels kept in shared memory.
 //   long rows (> FRX_SPLIT_MIN entries) are cut into pieces: MODE 1 dumps per-piece partial sums, MODE 2
 //            solves such a row from the sum of its pieces, MODE 0 is the ordinary row.
+//   GRAD     the CVaR-MF gradient steps (cvar_mf.h:88-180) take phase A as it is and replace phase B by
+//            x - step * (M x - rhs), evaluated from the TMEM-resident SYRK sum.
 //
 // Hardware conventions were established with tools/tc_probe.cu / tc_rate.cu / lat_probe.cu on a B200:
-//  * kind::tf32 works with K-major operands (SWIZZLE_128B, SBO = 1024 B, K step = +32 B on
+//  * kind::tf32 and kind::f16 work with K-major operands (SWIZZLE_128B, SBO = 1024 B, K step = +32 B on
 //    the descriptor start address); MN-major tf32 operands produce zeros, hence the transpose.
 //  * the MMA ignores the low 13 mantissa bits of fp32 inputs (truncation).
 //  * tcgen05.ld/st 32x32b: warp w touches TMEM lanes 32*(w%4)..+31, thread = accumulator row.
 //  * an M=128 MMA takes 93 / 106 / 170 cycles for N <= 64 / 128 / 256; the issuing thread blocks while
 //    the (shallow) tensor queue is full.
-// Restates ials.h:88-144, safer2.h:104-163 and safer2.h:166-221 (incl. the stale-tail quirk).
+// Restates ials.h:88-144, safer2.h:104-163, safer2.h:166-221 (incl. the stale-tail quirk) and cvar_mf.h:88-180.
 #include "frx_kernels.cuh"
 #include "frx_tc_common.cuh"
 #include <cstdint>

@@ -15,8 +15,9 @@
 // Roles inside the persistent CTA (one per SM, 18 warps):
 //   scheduler warp  takes group ids from a global atomic counter and publishes the group's slot descriptors
 //                   in a small shared-memory ring;
-//   4 loader warps  warp s = slot s of every group, its 32-feature chunks in order: lane = history entry,
-//                   128 contiguous bytes of the rotated factor row per chunk (next chunk prefetched), the
+//   4 loader warps  warp s = slot s of every group, its 32-feature chunks in order: the chunk of the 32 entries
+//                   arrives by line-coalesced cp.async in a swizzled per-warp buffer (next chunk in flight),
+//                   is read back with lane = history entry (128 bytes of the rotated factor row), the
 //                   bidiagonal forward recurrence w_j = sqrt(s) e_j - l_j w_(j-1) along the features, scaled by
 //                   Dl^(-1/2), split into tf32 hi + lo and stored as K-major SWIZZLE_128B operand tiles
 //                   [128 entries][32 features] (no transpose: the contraction runs over the features here);
