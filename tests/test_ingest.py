@@ -115,3 +115,50 @@ def test_large_file_is_parsed_in_parallel_in_file_order(tmp_path):
     n, mu, mi, users, items, _ = _load(tool, path, str(tmp_path))
     assert n == 300000 and np.array_equal(users, u) and np.array_equal(items, i)
     assert (mu, mi) == (int(u.max()), int(i.max()))
+
+
+def test_binary_cache_round_trip(tmp_path):
+    """FRECSYS_DATASET_CACHE=1 (binary cache of the parsed CSR input): the second load comes from
+    `<csv>.frxbin` and is identical; a changed CSV (size / mtime key) invalidates the cache; a damaged cache is
+    ignored; without the switch nothing is written next to the input."""
+    tool = _build_tool()
+    rng = np.random.default_rng(3)
+    path = os.path.join(tmp_path, "d.csv")
+    rows = [(int(u), int(i)) for u, i in zip(rng.integers(0, 300, 5000), rng.integers(0, 200, 5000))]
+    with open(path, "w") as f:
+        f.write("uid,sid\n" + "".join(f"{u},{i}\n" for u, i in rows))
+    n0, _, _, u0, i0, _ = _load(tool, path, tmp_path)
+    assert not os.path.exists(path + ".frxbin")
+    env = dict(os.environ, FRECSYS_DATASET_CACHE="1")
+
+    def load_cached():
+        out = os.path.join(tmp_path, "dump.bin")
+        subprocess.run([tool, path, out], check=True, capture_output=True, env=env)
+        raw = np.fromfile(out, dtype=np.int32)
+        n = int(raw[0])
+        return n, raw[3:3 + n].copy(), raw[3 + n:3 + 2 * n].copy()
+
+    n1, u1, i1 = load_cached()
+    assert os.path.exists(path + ".frxbin")
+    n2, u2, i2 = load_cached()          # from the cache
+    assert n0 == n1 == n2 == 5000
+    assert np.array_equal(u0, u1) and np.array_equal(u1, u2) and np.array_equal(i0, i1) and np.array_equal(i1, i2)
+    # the cache really is what gets read: poison its payload (same header) and load again
+    blob = bytearray(open(path + ".frxbin", "rb").read())
+    blob[32:36] = (12345).to_bytes(4, "little")
+    st = os.stat(path)
+    open(path + ".frxbin", "wb").write(bytes(blob))
+    os.utime(path, ns=(st.st_atime_ns, st.st_mtime_ns))
+    n3, u3, _ = load_cached()
+    assert n3 == 5000 and u3[0] == 12345
+    # a changed CSV invalidates it
+    with open(path, "a") as f:
+        f.write("7,9\n")
+    n4, u4, i4 = load_cached()
+    assert n4 == 5001 and u4[-1] == 7 and i4[-1] == 9 and u4[0] == rows[0][0]
+    # a truncated cache is ignored and rewritten
+    open(path + ".frxbin", "wb").write(open(path + ".frxbin", "rb").read()[:100])
+    n5, u5, _ = load_cached()
+    assert n5 == 5001 and np.array_equal(u5, u4)
+    n6, u6, _ = load_cached()
+    assert n6 == 5001 and np.array_equal(u6, u4)
