@@ -935,7 +935,7 @@ class Model {
     const int num_other = E.rows;
     ParallelFor((int)rows.size(), [&](int r) {
       const SpVector& h = rows[r];
-      if (h.empty()) return;
+      if (h.empty() || !InRange(r)) return;
       float* x = out->row(row_map ? (*row_map)[r] : r);
       if (safer) {
         float weight = weight_of ? weight_of[r] : 1.0f;
@@ -955,7 +955,7 @@ class Model {
     Mat lgg = GramianGeneral(U, bs, be - bs, U, 0, U.cols, dual_weight.data());
     ParallelFor((int)data.by_item.size(), [&](int v) {
       const SpVector& h = data.by_item[v];
-      if (h.empty()) return;
+      if (h.empty() || !InRange(v)) return;
       BlockUpdateRow(2, h, V.row(v), U, bs, be, lg, lgg, ItemReg(v, U.rows), 1.f,
                      norm_dual_weight.data(), pred);
     });

@@ -126,6 +126,8 @@ def lib():
         L.orc_num_threads.restype = C.c_int
         L.orc_model_set_range.argtypes = [vp, C.c_int, C.c_int]
         L.orc_model_put_factors.argtypes = [vp, fp, fp]
+        L.orc_model_block_step.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, fp]
+        L.orc_model_predict_rows.argtypes = [vp, vp, C.c_int, fp]
         L.orc_model_set_item_gramian.argtypes = [vp, fp]
         L.orc_model_set_gz_override.argtypes = [vp, fp]
         _lib = L
@@ -219,6 +221,16 @@ class Model:
     def set_gz_override(self, G):
         G = None if G is None else np.ascontiguousarray(G, np.float32)
         lib().orc_model_set_gz_override(self.h, _fp(G))
+
+    def block_step(self, ds, item_side, bs, be, pred):
+        """One ++ block sweep on the rows in range; `pred` (float32 [num_tuples]) is updated in place."""
+        assert pred.dtype == np.float32 and pred.flags.c_contiguous
+        lib().orc_model_block_step(self.h, ds.h, int(item_side), int(bs), int(be), _fp(pred))
+
+    def predict_rows(self, ds, item_side, pred):
+        """pred[t] = x_row . e_col for the tuples of the rows in range."""
+        assert pred.dtype == np.float32 and pred.flags.c_contiguous
+        lib().orc_model_predict_rows(self.h, ds.h, int(item_side), _fp(pred))
 
     def train(self, ds):
         lib().orc_model_train(self.h, ds.h)

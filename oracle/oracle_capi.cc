@@ -202,4 +202,29 @@ void orc_model_set_gz_override(void* mv, const float* G) {
   }
 }
 
+// One block sweep of a ++ model on the rows in [row_lo, row_hi) of one side (ialspp.h:351-424, safer2pp.h:448-609)
+// with the caller's prediction cache, and the refresh of that cache for the same rows from the current factors:
+// the two steps every rank of the multi-GPU block solvers performs (csrc/frx_api.cu stage_block).
+void orc_model_block_step(void* mv, void* dv, int item_side, int bs, int be, float* pred) {
+  Model* m = (Model*)mv;
+  Dataset& d = *(Dataset*)dv;
+  std::vector<float> p(pred, pred + d.num_tuples);
+  const bool safer = m->cfg.model == kSAFER2pp;
+  if (!item_side) m->StepBlockUserSide(d.by_user, &m->U, nullptr, m->V, bs, be, &p, safer, safer ? m->dual_weight.data() : nullptr);
+  else if (safer) m->StepBlockV_Safer(d, bs, be, &p);
+  else m->StepBlockUserSide(d.by_item, &m->V, nullptr, m->U, bs, be, &p, false, nullptr);
+  std::copy(p.begin(), p.end(), pred);
+}
+void orc_model_predict_rows(void* mv, void* dv, int item_side, float* pred) {
+  Model* m = (Model*)mv;
+  Dataset& d = *(Dataset*)dv;
+  const std::vector<SpVector>& rows = item_side ? d.by_item : d.by_user;
+  const Mat& X = item_side ? m->V : m->U;
+  const Mat& E = item_side ? m->U : m->V;
+  for (int r = 0; r < (int)rows.size(); ++r) {
+    if (!m->InRange(r)) continue;
+    for (const auto& ir : rows[r]) pred[ir.second] = (float)Dot(E.row(ir.first), X.row(r), E.cols);
+  }
+}
+
 }  // extern "C"

@@ -8,6 +8,7 @@ import os
 import sys
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -122,3 +123,88 @@ def test_row_sharded_epoch_world2_gloo(tmp_path):
     assert abs(float(got["xi"]) - st["xi"]) < 1e-5
     np.testing.assert_allclose(got["loss"], st["loss"], rtol=1e-4, atol=1e-7)
     assert 0 < got["ub"][1] < NU and 0 < got["ib"][1] < NI
+
+
+PP_CFG = dict(dim=16, block_size=8, uobs_weight=0.05, reg=0.01)
+
+
+def _pp_worker(rank, world, port, out_path, name):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, helpers.ROOT)
+    from oracle import loader as O
+    pkg = helpers.load_pkg()
+    users, items = _data()
+    ds = O.Dataset.from_tuples(users, items)
+    ub = pkg.partition_rows(ds.csr(0, NU)[0], world)
+    ib = pkg.partition_rows(ds.csr(1, NI)[0], world)
+    cfg = dict(PP_CFG, model=name)
+    if name == "safer2pp":
+        cfg.update(uobs_weight=0.004, reg=0.004, bandwidth=0.15)
+    m = O.Model(NU, NI, init_seed=21, **cfg)
+    m.initialize(ds)
+    umask = np.zeros((NU, 1), np.float32)
+    umask[ub[rank]:ub[rank + 1]] = 1
+    vmask = np.zeros((NI, 1), np.float32)
+    vmask[ib[rank]:ib[rank + 1]] = 1
+    d, B = cfg["dim"], cfg["block_size"]
+    pred = np.zeros(len(users), np.float32)       # replicated in memory, current only for the rows about to be solved
+    for _ in range(2):
+        if name == "safer2pp":
+            m.set_range(0, 2 ** 30)
+            m.stage(ds, 0)                                      # z (all users, safer2pp.h:847-856): replicated
+        for start in range(0, d, B):
+            end = min(start + B, d)
+            # csrc/frx_api.cu stage_block: refresh the cached predictions of this rank's rows, block sweep, all-gather
+            m.set_range(ub[rank], ub[rank + 1])
+            m.predict_rows(ds, 0, pred)
+            m.block_step(ds, 0, start, end, pred)
+            m.put_factors(U=_allsum(m.factors()[0] * umask))
+            m.set_range(ib[rank], ib[rank + 1])
+            m.predict_rows(ds, 1, pred)
+            m.block_step(ds, 1, start, end, pred)
+            m.put_factors(V=_allsum(m.factors()[1] * vmask))
+        if name == "safer2pp":
+            # item Gramian, per-user loss on own rows (from factors here: the product refreshes its cache and reads
+            # the same dot products), all-gather, xi replicated
+            V = m.factors()[1]
+            b, e = NI * rank // world, NI * (rank + 1) // world
+            m.set_item_gramian(_allsum(O.gramian(V[b:e])))
+            m.set_range(ub[rank], ub[rank + 1])
+            m.stage(ds, 4)
+            st = m.state()
+            m.set_state(z=st["z"], loss=_allsum(st["loss"] * umask[:, 0]), xi=st["xi"])
+            m.set_range(0, 2 ** 30)
+            m.stage(ds, 5)
+    U, V = m.factors()
+    if rank == 0:
+        np.savez(out_path, U=U, V=V, xi=m.state()["xi"])
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["ialspp", "safer2pp"])
+def test_block_solvers_row_sharded_world2_gloo(tmp_path, name):
+    """The multi-GPU protocol of the block-subspace models (csrc/frx_api.cu stage_block with several ranks): the
+    prediction cache is replicated in memory but only kept current for the rows a rank is about to solve (recomputed
+    from the all-gathered factors), the updated block is all-gathered after every sweep.  Two oracle processes
+    following that protocol over gloo must reproduce the single-process epoch (whose cache is incremental,
+    ialspp.h:136-143) to fp32 rounding."""
+    from oracle import loader as O
+    out = str(tmp_path / "pp.npz")
+    port = 29900 + os.getpid() % 90
+    mp.spawn(_pp_worker, args=(2, port, out, name), nprocs=2, join=True)
+    got = np.load(out)
+    users, items = _data()
+    ds = O.Dataset.from_tuples(users, items)
+    cfg = dict(PP_CFG, model=name)
+    if name == "safer2pp":
+        cfg.update(uobs_weight=0.004, reg=0.004, bandwidth=0.15)
+    m = O.Model(NU, NI, init_seed=21, **cfg)
+    m.initialize(ds)
+    for _ in range(2):
+        m.train(ds)
+    U, V = m.factors()
+    assert helpers.rel_fro(got["U"], U) < 2e-5, helpers.rel_fro(got["U"], U)
+    assert helpers.rel_fro(got["V"], V) < 2e-5, helpers.rel_fro(got["V"], V)
+    if name == "safer2pp":
+        assert abs(float(got["xi"]) - m.state()["xi"]) < 1e-4
