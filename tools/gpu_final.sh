@@ -1,3 +1,5 @@
+#!/bin/bash
+# Round-end verification on one B200: gpurun -- "bash tools/gpu_final.sh" -> pytest -m gpu, smoke(), default bench.
 mkdir -p gpurun_out
 (timeout 1200 python -m pytest tests -q -m gpu --timeout 400 2>&1 | tail -25) > gpurun_out/final_tests.log
 tail -6 gpurun_out/final_tests.log

@@ -1,3 +1,6 @@
+#!/bin/bash
+# Multi-GPU checks on one box: gpurun --gpus N -- "bash tools/gpu_multi.sh N" -> dist_parity log, bench lines
+# (point-to-point and broadcast all-gather), one iALS++ line.
 mkdir -p gpurun_out
 N=${1:-8}
 (DIST_PARITY_CASES="safer2:256,safer2:128,ialspp:32,safer2pp:128,cvar_mf:32" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tests/dist_parity.py 2>&1 | grep "dist_parity" ) > gpurun_out/dist_parity_n$N.log
