@@ -48,6 +48,8 @@ CASES = {
     "ials_d128_e1": ("ials", 128, 1, dict(uobs_weight=0.2, reg=0.006)),
     "ialspp_d128_b64_e1": ("ialspp", 128, 1, dict(uobs_weight=0.1, reg=0.003, block_size=64)),
     "safer2pp_d128_b64_e1": ("safer2pp", 128, 1, dict(uobs_weight=0.004, reg=0.004, bandwidth=0.15, block_size=64)),
+    # CVaR-MF at d = 128: the gradient-step variant of the tensor-core row kernel; the second epoch has z in {0, 1}
+    "cvar_mf_d128_e2": ("cvar_mf", 128, 2, dict(uobs_weight=0.008, reg=0.002, stepsize=0.4)),
 }
 
 
