@@ -161,8 +161,8 @@ def cpu_baseline_sample(args, users, items, num_users, num_items, cfg, frac=0.01
     threads (the reference's thread model): the row-wise stages (StepU + ComputeUserLoss, StepV) run on the full
     histories of `frac` of the users / items and are scaled by the row counts; the stages that do not shard by
     row (the weighted Gramian U^T diag(z) U over all users, V^T V, the xi Newton iterations, the z update) run at
-    full size.  Returns the epoch-equivalent row-solves/s.  Built with -DORACLE_FAST (cache-blocked SYRK,
-    vectorised Cholesky dots: the shape of Eigen's kernels; timing-only, see oracle/frecsys_oracle.hpp)."""
+    full size.  Returns the epoch-equivalent row-solves/s.  Built with -DORACLE_FAST (register-blocked SYRK,
+    right-looking blocked Cholesky: the shape of Eigen's kernels; timing-only, see oracle/frecsys_oracle.hpp)."""
     os.environ["FRECSYS_ORACLE_FAST"] = "1"   # before the first import of the loader in this process
     from oracle import loader as O
     rng = np.random.default_rng(4242)
@@ -215,8 +215,8 @@ def cpu_baseline_sample(args, users, items, num_users, num_items, cfg, frac=0.01
             "sample": f"{frac:.0%} of users (StepU+ComputeUserLoss, {dsA.num_tuples} tuples) + {frac:.0%} of items "
                       f"(StepV, {dsB.num_tuples} tuples) scaled by row count, plus the full-size weighted Gramian, "
                       f"V^T V, z update and xi iterations; Eigen-free CPU restatement of the reference (Eigen is "
-                      f"not in the image) in its timing build (-O3 -march=native -DORACLE_FAST: cache-blocked "
-                      f"SYRK, vectorised Cholesky), {cores} threads. A stated baseline, not Eigen itself."}
+                      f"not in the image) in its timing build (-O3 -march=native -DORACLE_FAST: register-blocked "
+                      f"SYRK, right-looking blocked Cholesky), {cores} threads. A stated baseline, not Eigen itself."}
 
 
 def main():
